@@ -1,0 +1,310 @@
+"""TEST INFRASTRUCTURE -- drives the UNMODIFIED reference engine (/root/reference) with an injected
+counter-based Philox stream and serialises its object graph into the packed state of sb_layout.py.
+
+Only usable in the build container (the reference does not travel to the GPU box).  Used by
+tests/golden/make_golden.py (fixture generation) and oracle/validate_vs_reference.py (live check of
+the C oracle).  Nothing in the product package imports this module.
+
+Reference entry points exercised: games/stormbound.py:293-373 (Stormbound ctor/step),
+:528-557 (legal_actions), player.py:13-37, board.py:16-28.
+"""
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("SB_REFERENCE", "/root/reference")
+
+from sb_layout import (STATE_DTYPE, CF_FIXED, CF_SINGLE_USE, PF_LEFTMOST_MOVABLE, PF_REPLACABLE, ST_BITS,
+                       TF_FIXED, TF_OWNER, TF_STRUCTURE, weight_table, fnv1a64)  # noqa: E402
+
+M32 = 0xFFFFFFFF
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox-4x32-10 (Salmon et al., SC'11), the published round function and Weyl constants."""
+    for _ in range(10):
+        p0 = 0xD2511F53 * c0
+        p1 = 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & M32, p1 & M32, ((p0 >> 32) ^ c3 ^ k1) & M32, p0 & M32
+        k0 = (k0 + 0x9E3779B9) & M32
+        k1 = (k1 + 0xBB67AE85) & M32
+    return c0, c1, c2, c3
+
+
+class PhiloxRandomState:
+    """Drop-in for the 5 call shapes the rules engine uses on np.random.RandomState.
+
+    Stream: word block = philox(counter=(draw, turn, 0, 0), key=(seed_lo, seed_hi)); every call
+    consumes exactly one block (shuffle of n: n-1 blocks).  Plain attributes -> copy.deepcopy clones the
+    stream position, as evo/game_adapter.py:284 relies on.
+    """
+
+    def __init__(self, seed):
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.turn = 0
+        self.draw = 0
+        self.calls = 0
+
+    def _block(self):
+        out = philox4x32_10(self.draw & M32, self.turn & M32, 0, 0, self.seed & M32, self.seed >> 32)
+        self.draw += 1
+        self.calls += 1
+        return out
+
+    def _below(self, n):
+        if n <= 0:
+            raise ValueError("empty range")
+        return (self._block()[0] * n) >> 32
+
+    def random(self):
+        w = self._block()
+        return ((w[0] >> 5) * 67108864 + (w[1] >> 6)) / 9007199254740992.0
+
+    def randint(self, low, high=None):
+        if high is None:
+            low, high = 0, low
+        return low + self._below(high - low)
+
+    def shuffle(self, seq):
+        for i in range(len(seq) - 1, 0, -1):
+            j = self._below(i + 1)
+            seq[i], seq[j] = seq[j], seq[i]
+
+    def choice(self, seq, size=None, p=None):
+        seq = list(seq)
+        if len(seq) == 0:
+            raise ValueError("'a' cannot be empty unless no samples are taken")
+        if p is None:
+            assert size is None
+            return seq[self._below(len(seq))]
+        # numpy legacy choice(p=): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, side="right")
+        assert size == 1
+        cdf = []
+        acc = 0.0
+        for q in p:
+            acc = acc + q
+            cdf.append(acc)
+        last = cdf[-1]
+        u = self.random()
+        idx = 0
+        for c in cdf:
+            if c / last <= u:
+                idx += 1
+        return [seq[min(idx, len(seq) - 1)]]
+
+
+def agent_pick(seed, step, n):
+    """Uniform-random agent stream: philox(counter=(step,0,0xA6E7,0), key=seed)."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    w = philox4x32_10(step & M32, 0, 0xA6E7, 0, seed & M32, seed >> 32)
+    return (w[0] * n) >> 32
+
+
+_ref = None
+
+
+def ref():
+    """Import the reference once (flat module names, cwd-relative opens: games/stormbound.py:306-310)."""
+    global _ref
+    if _ref is not None:
+        return _ref
+    if not os.path.isdir(REF):
+        raise RuntimeError("reference not available at %s" % REF)
+    for p in (REF, os.path.join(HERE, "refshim")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    try:
+        import cards as c
+        import games.stormbound as gs
+        import board, player, unit, structure, spell, enums, point  # noqa: E401
+    finally:
+        os.chdir(cwd)
+
+    class NS:
+        pass
+
+    ns = NS()
+    ns.cards, ns.gs, ns.board, ns.player, ns.unit = c, gs, board, player, unit
+    ns.structure, ns.spell, ns.enums, ns.point = structure, spell, enums, point
+    sys.path.insert(0, os.path.dirname(HERE))
+    from monsoon_b200._card_table import CARDS
+    ns.table = CARDS
+    ns.index = {r["name"]: i for i, r in enumerate(CARDS)}
+    with open(os.path.join(REF, "actions.txt")) as f:
+        ns.actions = f.read().splitlines()
+    ns.wn = {float(w): n for n, w in enumerate(weight_table())}
+    _ref = ns
+    return ns
+
+
+DEFAULT_DECKS = (
+    ["UA07", "U007", "U306", "U061", "B304", "U305", "U320", "U302", "U313", "UA02", "UT32", "U316"],
+    ["UA07", "U007", "U001", "U053", "UE01", "U211", "U206", "U071", "U020", "S013", "B001", "U061"],
+)
+DEFAULT_FACTIONS = (3, 2)  # IRONCLAD, SWARM (games/stormbound.py:295,299)
+
+
+def make_game(seed, decks=None, factions=None):
+    """Repeat games/stormbound.py:293-310 with the Philox stream in place BEFORE the Player
+    constructors run (they shuffle and draw, player.py:28,35).  Returns a reference `Game`."""
+    r = ref()
+    gs = r.gs
+    decks = decks or DEFAULT_DECKS
+    factions = factions or DEFAULT_FACTIONS
+    rnd = PhiloxRandomState(seed)
+
+    class TurnCountingStormbound(gs.Stormbound):
+        def step(self, action):  # the reference has no turn counter; the stream is keyed by it
+            if action == 155:
+                self.random.turn += 1
+                self.random.draw = 0
+            return super().step(action)
+
+    env = TurnCountingStormbound.__new__(TurnCountingStormbound)
+    env.random = rnd
+    mk = lambda names: [getattr(r.cards, n)() for n in names]  # noqa: E731
+    local = r.player.Player(r.enums.Faction(factions[0]), mk(decks[0]), r.enums.PlayerOrder.FIRST, rnd)
+    remote = r.player.Player(r.enums.Faction(factions[1]), mk(decks[1]), r.enums.PlayerOrder.SECOND, rnd)
+    env.board = r.board.Board(local, remote, rnd)
+    env.player = 1
+    env.actions = r.actions
+    env.cards = []
+    env.n_steps = 0
+    game = gs.Game.__new__(gs.Game)
+    game.env = env
+    return game
+
+
+def card_index(card):
+    r = ref()
+    cid = card.card_id
+    if cid[0] == "f":
+        return 113 + int(cid[1:])
+    name = type(card).__name__.upper()
+    if name in r.index:
+        return r.index[name]
+    if isinstance(card, r.structure.Structure):
+        return 129
+    raise KeyError(cid)
+
+
+def _status_word(unit):
+    w = 0
+    for s in unit.status_effects:
+        w += 1 << (ST_BITS * int(s))
+    return w
+
+
+def pack_reference(game, steps=0, done=0, err=0):
+    """Serialise the reference object graph into one packed 512-byte state."""
+    r = ref()
+    env = game.env
+    b = env.board
+    s = np.zeros((), dtype=STATE_DTYPE)
+    s["seed_lo"] = env.random.seed & M32
+    s["seed_hi"] = env.random.seed >> 32
+    s["turn"] = env.random.turn
+    s["draw"] = env.random.draw
+    s["steps"] = steps
+    s["local_order"] = int(b.local.order)
+    s["current_order"] = int(b.current_player.order)
+    s["player_sign"] = env.player
+    s["phase"] = int(b.phase)
+    s["err"] = err
+    s["done"] = done
+    hist = b.history[-4:]
+    s["hist_n"] = len(hist)
+    for i, c in enumerate(hist):
+        s["hist_card"][i] = card_index(c)
+        s["hist_owner"][i] = int(c.player.order)
+    for pl in (b.local, b.remote):
+        p = s["pl"][int(pl.order)]
+        p["base"], p["max_mana"], p["mana"] = pl.strength, pl.max_mana, pl.current_mana
+        p["front_line"] = pl.front_line
+        p["flags"] = (PF_REPLACABLE if pl.replacable else 0) | (PF_LEFTMOST_MOVABLE if pl.leftmost_movable else 0)
+        p["n_hand"], p["n_deck"], p["faction"] = len(pl.hand), len(pl.deck), int(pl.faction)
+        for i, c in enumerate(pl.hand):
+            p["hand_card"][i] = card_index(c)
+            p["hand_cost"][i] = c.cost
+            p["hand_flags"][i] = (CF_FIXED if getattr(c, "fixedly_forward", False) else 0) | \
+                                 (CF_SINGLE_USE if c.is_single_use else 0)
+        for i, c in enumerate(pl.deck):
+            p["deck_card"][i] = card_index(c)
+            p["deck_cost"][i] = c.cost
+            p["deck_flags"][i] = (CF_FIXED if getattr(c, "fixedly_forward", False) else 0) | \
+                                 (CF_SINGLE_USE if c.is_single_use else 0)
+            p["deck_wn"][i] = r.wn[float(c.weight)]
+    for y in range(5):
+        for x in range(4):
+            e = b.board[y][x]
+            if e is None:
+                continue
+            t = s["tile"][y * 4 + x]
+            t["card"] = card_index(e)
+            is_struct = isinstance(e, r.structure.Structure)
+            t["flags"] = (TF_OWNER if int(e.player.order) else 0) | (TF_STRUCTURE if is_struct else 0) | \
+                         (TF_FIXED if getattr(e, "fixedly_forward", False) else 0)
+            t["strength"] = e.strength
+            t["status"] = 0 if is_struct else _status_word(e)
+    return s
+
+
+def legal_mask(actions):
+    m = np.zeros(5, dtype=np.uint32)
+    for a in actions:
+        m[a >> 5] |= np.uint32(1 << (a & 31))
+    return m
+
+
+@contextlib.contextmanager
+def quiet():
+    """cards/u040.py:14 prints inside the ability."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def play_random_game(seed, decks=None, factions=None, max_steps=400, record=True):
+    """Uniform-random legal agent (agent_pick stream) until `done` or max_steps.
+
+    Returns dict(actions u8[n], masks u32[n,5] (legal set BEFORE each action), digests u64[n]
+    (fnv1a64 of the packed state AFTER each action), states (list of packed states if record),
+    init packed state, err flag (an exception escaped step), final packed state).
+    """
+    game = make_game(seed, decks, factions)
+    env = game.env
+    init = pack_reference(game)
+    actions, masks, digests, states, rewards, dones = [], [], [], [], [], []
+    err = 0
+    done = False
+    step = 0
+    with quiet():
+        while not done and step < max_steps:
+            legal = game.legal_actions()
+            a = legal[agent_pick(seed, step, len(legal))]
+            try:
+                _obs, reward, done = game.step(a)
+            except Exception as e:  # noqa: BLE001 -- the reference's callers swallow these (Q11)
+                err = 1
+                actions.append(a)
+                masks.append(legal_mask(legal))
+                break
+            step += 1
+            st = pack_reference(game, steps=step, done=(1 if done else 0) | (2 if reward else 0))
+            actions.append(a)
+            masks.append(legal_mask(legal))
+            digests.append(fnv1a64(st.tobytes()))
+            rewards.append(reward)
+            dones.append(done)
+            if record:
+                states.append(st)
+    final = pack_reference(game, steps=step, done=(1 if done else 0))
+    return dict(seed=seed, init=init, actions=np.array(actions, dtype=np.uint8),
+                masks=np.array(masks, dtype=np.uint32).reshape(-1, 5),
+                digests=np.array(digests, dtype=np.uint64), states=states, err=err, final=final,
+                n_steps=step, done=bool(done), game=game)

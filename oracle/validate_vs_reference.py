@@ -1,0 +1,117 @@
+#!/usr/bin/env python3
+"""TEST INFRASTRUCTURE -- live check of the C oracle against the UNMODIFIED reference engine.
+
+Runs only in the build container.  For every seed: build the game through the reference with the
+injected Philox stream, play the uniform-random agent, and compare the packed state after EVERY step
+(and the legal set before every step) with the oracle stepping the same actions.
+
+  python oracle/validate_vs_reference.py --seeds 0:200            # default decks
+  python oracle/validate_vs_reference.py --seeds 0:200 --random-decks
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as h  # noqa: E402
+import sb_oracle as o  # noqa: E402
+from sb_layout import STATE_DTYPE  # noqa: E402
+
+
+def diff_states(a, b):
+    sa = np.frombuffer(a.tobytes(), dtype=STATE_DTYPE)[0]
+    sb = np.frombuffer(b.tobytes(), dtype=STATE_DTYPE)[0]
+    out = []
+    for name in STATE_DTYPE.names:
+        if name in ("pl", "tile"):
+            for i in range(len(sa[name])):
+                for sub in sa[name].dtype.names:
+                    if not np.array_equal(sa[name][i][sub], sb[name][i][sub]):
+                        out.append("%s[%d].%s ref=%s oracle=%s" % (name, i, sub, sa[name][i][sub], sb[name][i][sub]))
+        elif not np.array_equal(sa[name], sb[name]):
+            out.append("%s ref=%s oracle=%s" % (name, sa[name], sb[name]))
+    return out
+
+
+def check_seed(seed, decks=None, factions=None, max_steps=400, verbose=True):
+    r = h.ref()
+    decks = decks or h.DEFAULT_DECKS
+    factions = factions or h.DEFAULT_FACTIONS
+    tape = h.play_random_game(seed, decks, factions, max_steps=max_steps, record=True)
+    d0 = [r.index[n] for n in decks[0]]
+    d1 = [r.index[n] for n in decks[1]]
+    st = o.new_game(seed, d0, d1, factions[0], factions[1])
+    if st.tobytes() != tape["init"].tobytes():
+        if verbose:
+            print("seed", seed, "INIT mismatch", diff_states(tape["init"], st))
+        return False, 0, tape
+    for k in range(tape["n_steps"]):
+        m = o.legal_mask(st)
+        if not np.array_equal(m, tape["masks"][k]):
+            if verbose:
+                print("seed", seed, "step", k, "LEGAL mismatch ref", tape["masks"][k], "oracle", m)
+            return False, k, tape
+        o.step(st, int(tape["actions"][k]))
+        if st.tobytes() != tape["states"][k].tobytes():
+            if verbose:
+                print("seed", seed, "step", k, "action", tape["actions"][k], "STATE mismatch")
+                for line in diff_states(tape["states"][k], st)[:12]:
+                    print("   ", line)
+            return False, k, tape
+    if tape["err"]:
+        o.step(st, int(tape["actions"][-1]))
+        if not st[18]:
+            if verbose:
+                print("seed", seed, "reference raised at step", tape["n_steps"], "oracle did not")
+            return False, tape["n_steps"], tape
+    return True, tape["n_steps"], tape
+
+
+def random_decks(seed, exclude=("UP01", "UP02", "UP03")):
+    """generate_random_deck semantics (utils.py:26-119): 12 distinct classes from faction + NEUTRAL."""
+    import random
+    r = h.ref()
+    rng = random.Random(seed)
+    decks, factions = [], []
+    for _side in range(2):
+        faction = rng.choice([1, 2, 3, 4])
+        pool = [c["name"] for c in r.table[1:113] if c["faction"] in (0, faction) and c["name"] not in exclude]
+        decks.append(rng.sample(pool, 12))
+        factions.append(faction)
+    return decks, factions
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", default="0:50")
+    ap.add_argument("--random-decks", action="store_true")
+    ap.add_argument("--exclude", default="UP01,UP02,UP03")
+    ap.add_argument("--max-steps", type=int, default=400)
+    args = ap.parse_args()
+    lo, hi = (int(x) for x in args.seeds.split(":"))
+    ok = bad = steps = errs = 0
+    t0 = time.time()
+    for seed in range(lo, hi):
+        if args.random_decks:
+            decks, factions = random_decks(seed, tuple(args.exclude.split(",")))
+        else:
+            decks, factions = None, None
+        good, n, tape = check_seed(seed, decks, factions, args.max_steps)
+        steps += n
+        errs += tape["err"]
+        if good:
+            ok += 1
+        else:
+            bad += 1
+            if args.random_decks:
+                print("   decks", decks)
+    print("seeds %d:%d ok=%d bad=%d steps=%d ref_exceptions=%d  %.1fs" % (lo, hi, ok, bad, steps, errs, time.time() - t0))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
