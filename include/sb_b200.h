@@ -1,0 +1,95 @@
+/* sb_b200.h -- C ABI of libsb_b200.so, the B200 (sm_100a) batched Stormbound simulator.
+ *
+ * The reference has no FFI: its boundary is three Python class contracts.  Every entry
+ * point below names the reference interface it replaces; the Python shims in monsoon_b200/ (Game,
+ * StormboundAdapter, HeuristicAgent, FitnessEvaluator) bind these with ctypes and keep the reference's
+ * signatures.  INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions: plain C types only; every `*_d` pointer is a DEVICE pointer owned by the caller (e.g.
+ * torch tensor .data_ptr()); `stream` is a cudaStream_t passed as void* (NULL = default stream); calls
+ * are asynchronous on that stream unless named *_host; return 0 on success, a negative CUDA error
+ * code otherwise (sb_last_error gives the text); no hidden allocation after sb_create except the
+ * *_host helpers' staging buffers; one handle per device, not thread-safe.
+ * There is NO CPU fallback: without a CUDA device sb_create fails.
+ */
+#ifndef SB_B200_H
+#define SB_B200_H
+#include <stdint.h>
+#include "sb_state.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct SbHandle SbHandle;
+
+/* library / layout introspection (no GPU needed) */
+int sb_abi_version(void);
+int sb_state_bytes(void);                 /* == SB_STATE_BYTES */
+int sb_card_count(void);                  /* rows of the card table (130) */
+int sb_card_info(int card, int32_t out[12]); /* kind,faction,cost,strength,movement,trigger,fixed,has_ability,first_type,types,obs_id,has_target */
+
+int sb_create(int device, SbHandle **out);
+int sb_destroy(SbHandle *h);
+const char *sb_last_error(SbHandle *h);
+int sb_device(SbHandle *h);
+int sb_sm_count(SbHandle *h);
+/* kernels launched through this handle so far (bench.py's gpu_launches) */
+uint64_t sb_launch_count(SbHandle *h);
+
+/* Stormbound.__init__ + Player.__init__ + Board.__init__ (games/stormbound.py:293-304, player.py:13-37,
+ * board.py:16-28): shuffle both 12-card decks, weights, draw 4, base 20, mana 3/4.
+ * decks_d: u8[n,2,n_deck] card indices, or u8[2,n_deck] when decks_shared; factions_d: u8[n,2] or u8[2]. */
+int sb_reset(SbHandle *h, int n, const uint64_t *seeds_d, const uint8_t *decks_d, int n_deck, int decks_shared,
+             const uint8_t *factions_d, uint8_t *states_d, void *stream);
+
+/* Stormbound.legal_actions (games/stormbound.py:528-557) -> 156-bit mask per game, u32[n,5] */
+int sb_legal_mask(SbHandle *h, int n, const uint8_t *states_d, uint32_t *masks_d, void *stream);
+
+/* Stormbound.step (games/stormbound.py:318-373): apply actions_d[n]; reward {0,1} (Game.step multiplies
+ * by 10, :140), done, err (non-zero = the reference raises here); next_masks_d (nullable) = legal set
+ * of the resulting state, fused into the same pass. */
+int sb_step(SbHandle *h, int n, uint8_t *states_d, const uint8_t *actions_d, int8_t *reward_d, uint8_t *done_d,
+            uint8_t *err_d, uint32_t *next_masks_d, void *stream);
+
+/* Stormbound.get_observation (games/stormbound.py:400-526): i32[n,27,5,4] */
+int sb_observe(SbHandle *h, int n, const uint8_t *states_d, int32_t *obs_d, uint8_t *err_d, void *stream);
+
+/* StateFeatures(obs).get_feature_vector() (evo/features.py:12-342): f64[n,10] */
+int sb_features(SbHandle *h, int n, const uint8_t *states_d, double *feat_d, uint8_t *err_d, void *stream);
+
+/* HeuristicAgent.select_action / score_action (evo/heuristic_agent.py:23-80) on StormboundAdapter forks
+ * (evo/game_adapter.py:280-324): weights_d f64[n,10]; actions_d u8[n]; scores_d (nullable) f64[n,156],
+ * NaN for illegal actions.  One warp per game, one lane per candidate action. */
+int sb_select_action(SbHandle *h, int n, const uint8_t *states_d, const double *weights_d, uint8_t *actions_d,
+                     double *scores_d, void *stream);
+
+/* Uniform-random legal agent until done/err or max_steps more steps (the agent
+ * stream is philox(counter=(step,0,0xA6E7,0), key=seed)).  steps_d i32[n] = steps taken by this call;
+ * chain_d (nullable) u64[n] = running hash of the per-step state digests (parity evidence). */
+int sb_rollout_random(SbHandle *h, int n, uint8_t *states_d, int max_steps, int32_t *steps_d, uint64_t *chain_d,
+                      void *stream);
+
+/* FitnessEvaluator._play_game (evo/fitness.py:178-228) with the intended loop (until have_winner or
+ * max_steps env steps): FIRST plays w_first_d[idx_first_d[g]], SECOND w_second_d[idx_second_d[g]]
+ * (idx arrays nullable = row g... row 0 when the weight table has one row is expressed by idx).
+ * result_d i8[n]: 0 FIRST won, 1 SECOND won, -1 draw/timeout, -2 aborted by an engine exception. */
+int sb_rollout_heuristic(SbHandle *h, int n, uint8_t *states_d, const double *w_first_d, const double *w_second_d,
+                         const int32_t *idx_first_d, const int32_t *idx_second_d, int max_steps, int8_t *result_d,
+                         int32_t *steps_d, void *stream);
+
+/* FitnessEvaluator.evaluate_population inner reduction (evo/fitness.py:95,160-166): counts_d i32[P,3]
+ * += {wins, draws, losses} of individual idx_first_d[g] over the n finished games. */
+int sb_accumulate_fitness(SbHandle *h, int n, const int8_t *result_d, const int32_t *idx_first_d, int32_t *counts_d,
+                          void *stream);
+
+/* Host-buffer variants (pinned or pageable host memory; H2D + kernel + D2H + sync inside): the e2e path. */
+int sb_step_host(SbHandle *h, int n, uint8_t *states, const uint8_t *actions, int8_t *reward, uint8_t *done,
+                 uint8_t *err, uint32_t *next_masks);
+int sb_rollout_random_host(SbHandle *h, int n, const uint64_t *seeds, const uint8_t *decks, int n_deck,
+                           const uint8_t *factions, int max_steps, uint8_t *states_out, int32_t *steps_out,
+                           uint64_t *chain_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -27,6 +27,7 @@
 /* hand / deck card flags */
 #define SB_CF_FIXED 1           /* Unit.fixedly_forward of the card object (cards/b008.py:15-16) */
 #define SB_CF_SINGLE_USE 2      /* Card.is_single_use (cards/ua20.py:31) */
+#define SB_CF_OBJ 4             /* the record IS a (former) board instance of B305 (cards/b305.py:41-45); see ext */
 /* tile flags */
 #define SB_TF_OWNER 1
 #define SB_TF_STRUCTURE 2
@@ -94,6 +95,9 @@ typedef struct SbState {
   uint8_t pad[3];
   SbPlayer pl[2];
   SbTile tile[SB_N_TILES];
+  /* ext[0] = n B005 memories, ext[1..90] = 9 x {temple tile, pos, card, tile flags, strength i16, status u32}
+   * (cards/b005.py:13,24-33); ext[91] = n board-instance card records, ext[92..107] = 4 x {order<<7 |
+   * in_deck<<6 | index, tile or 0xFF, frozen strength i16} (cards/b305.py:41-45). */
   uint8_t ext[SB_EXT_BYTES];
 } SbState;
 

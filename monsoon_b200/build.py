@@ -1,0 +1,28 @@
+"""Build libsb_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libsb_b200.so")
+SOURCES = ["sb_kernels.cu"]
+DEPS = SOURCES + ["sb_engine.cuh", "sb_effects.cuh", "sb_state_io.cuh", "sb_card_table.inc", "sb_card_ids.h",
+                  os.path.join("..", "..", "include", "sb_b200.h"), os.path.join("..", "..", "include", "sb_state.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build_library(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO] + SOURCES
+    subprocess.check_call(cmd, cwd=CSRC)
+    return SO

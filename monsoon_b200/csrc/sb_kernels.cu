@@ -1,0 +1,526 @@
+// sb_kernels.cu -- sm_100a kernels and the C ABI of libsb_b200.so (include/sb_b200.h).
+//
+// Kernels
+//   k_reset            one game per thread: shuffle, weights, opening hands (games/stormbound.py:293-304)
+//   k_legal_mask       one game per thread -> 156-bit mask (games/stormbound.py:528-557)
+//   k_step             one game per thread: unpack, Stormbound.step, pack, fused next legal mask
+//   k_observe/k_features  one game per thread
+//   k_rollout_random   one game per thread, whole rollout in one launch (state never leaves the SM)
+//   k_select_action    one WARP per game, one lane per candidate action (fork, step, features, score,
+//                      warp arg-max by shuffles) -- evo/heuristic_agent.py:53-80
+//   k_rollout_heuristic  one warp per game, whole game in one launch, base state staged in shared memory
+//   k_accumulate_fitness win/draw/loss counts per individual (evo/fitness.py:95,160-166)
+// State is AoS [n][512 B]; every thread (or warp) moves its record with 128-bit loads/stores; the card
+// table (130 x 24 B) is staged in shared memory once per CTA.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+#include "../../include/sb_b200.h"
+#include "sb_effects.cuh"
+#include "sb_state_io.cuh"
+
+#define SB_ABI_VERSION 1
+#define TPB_GAME 64      // threads per CTA for thread-per-game kernels
+#define WARPS_PER_CTA 4  // games per CTA for warp-per-game kernels
+
+// ---------------------------------------------------------------- helpers
+SBD_FI void stage_cards(DCard* s_cards, const DCard* cards) {
+  const u32* src = reinterpret_cast<const u32*>(cards);
+  u32* dst = reinterpret_cast<u32*>(s_cards);
+  for (int i = threadIdx.x; i < (int)(SBC_COUNT * sizeof(DCard) / 4); i += blockDim.x) dst[i] = __ldg(src + i);
+  __syncthreads();
+}
+SBD_FI void init_g(G& g, const DCard* s_cards, const double* wt) { g.cards = s_cards; g.wt = wt; }
+
+// ---------------------------------------------------------------- thread-per-game kernels
+__global__ void __launch_bounds__(TPB_GAME) k_reset(int n, const unsigned long long* seeds, const u8* decks, int n_deck,
+                                                    int decks_shared, const u8* factions, u8* states, const DCard* cards,
+                                                    const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  stage_cards(s_cards, cards);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G g;
+  init_g(g, s_cards, wt);
+  SbState s;
+  uint4* z = reinterpret_cast<uint4*>(&s);
+  for (int k = 0; k < SB_STATE_BYTES / 16; k++) z[k] = make_uint4(0, 0, 0, 0);
+  unpack(g, s);
+  unsigned long long seed = seeds[i];
+  g.seed_lo = (u32)seed; g.seed_hi = (u32)(seed >> 32);
+  g.local_order = 0; g.current_order = 0; g.player_sign = 1; g.phase = PH_PLAY;
+  const u8* dk = decks + (decks_shared ? 0 : (size_t)i * 2 * n_deck);
+  const u8* fc = factions + (decks_shared ? 0 : (size_t)i * 2);
+  for (int o = 0; o < 2; o++) {
+    Ply& p = g.pl[o];
+    p.max_mana = o == 0 ? 3 : 4; p.mana = p.max_mana; p.base = 20; p.front_line = o == 0 ? 4 : 0;
+    p.replacable = 1; p.leftmost = 1; p.faction = fc[o]; p.n_hand = 0;
+    i8 order[SB_DECK_MAX];
+    int nd = n_deck < SB_DECK_MAX ? n_deck : SB_DECK_MAX;
+    for (int k = 0; k < nd; k++) order[k] = (i8)dk[o * n_deck + k];
+    shuffle(g, order, nd);  // player.py:28
+    p.n_deck = (u8)nd;
+    for (int k = 0; k < nd; k++) {  // player.py:30-32
+      CardRec& c = p.deck[k];
+      c.card = (u8)order[k]; c.cost = CARD(g, c.card).cost; c.flags = (CARD(g, c.card).flags & DCF_FIXED) ? SB_CF_FIXED : 0;
+      c.link = -1; c.wn = (u16)k; c.xstr = 0;
+    }
+    player_fill_hand(g, o);  // player.py:35
+  }
+  pack(g, s);
+  store_state(states + (size_t)i * SB_STATE_BYTES, s);
+}
+
+__global__ void __launch_bounds__(TPB_GAME) k_legal_mask(int n, const u8* states, u32* masks, const DCard* cards, const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  stage_cards(s_cards, cards);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G g;
+  init_g(g, s_cards, wt);
+  SbState s;
+  load_state(s, states + (size_t)i * SB_STATE_BYTES);
+  unpack(g, s);
+  u32 m[SB_MASK_WORDS];
+  legal_mask(g, m);
+  for (int k = 0; k < SB_MASK_WORDS; k++) masks[(size_t)i * SB_MASK_WORDS + k] = m[k];
+}
+
+__global__ void __launch_bounds__(TPB_GAME) k_step(int n, u8* states, const u8* actions, i8* reward, u8* done, u8* err,
+                                                   u32* next_masks, const DCard* cards, const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  stage_cards(s_cards, cards);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G g;
+  init_g(g, s_cards, wt);
+  SbState s;
+  load_state(s, states + (size_t)i * SB_STATE_BYTES);
+  unpack(g, s);
+  game_step(g, actions[i]);
+  pack(g, s);
+  store_state(states + (size_t)i * SB_STATE_BYTES, s);
+  if (reward) reward[i] = (g.done & SB_REWARD) ? 1 : 0;
+  if (done) done[i] = (g.done & SB_DONE) ? 1 : 0;
+  if (err) err[i] = s.err;
+  if (next_masks) {
+    u32 m[SB_MASK_WORDS];
+    legal_mask(g, m);
+    for (int k = 0; k < SB_MASK_WORDS; k++) next_masks[(size_t)i * SB_MASK_WORDS + k] = m[k];
+  }
+}
+
+__global__ void __launch_bounds__(TPB_GAME) k_observe(int n, const u8* states, int* obs, u8* err, const DCard* cards, const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  stage_cards(s_cards, cards);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G g;
+  init_g(g, s_cards, wt);
+  SbState s;
+  load_state(s, states + (size_t)i * SB_STATE_BYTES);
+  unpack(g, s);
+  int e = observe(g, obs + (size_t)i * SB_OBS_INTS);
+  if (err) err[i] = (u8)e;
+}
+
+__global__ void __launch_bounds__(TPB_GAME) k_features(int n, const u8* states, double* feat, u8* err, const DCard* cards, const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  stage_cards(s_cards, cards);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G g;
+  init_g(g, s_cards, wt);
+  SbState s;
+  load_state(s, states + (size_t)i * SB_STATE_BYTES);
+  unpack(g, s);
+  double f[SB_N_FEATURES];
+  int e = features(g, f);
+  for (int k = 0; k < SB_N_FEATURES; k++) feat[(size_t)i * SB_N_FEATURES + k] = f[k];
+  if (err) err[i] = (u8)e;
+}
+
+// whole uniform-random rollout in one launch; HBM is touched once on the way in and once on the way out
+template <bool DIGEST>
+__global__ void __launch_bounds__(TPB_GAME) k_rollout_random(int n, u8* states, int max_steps, int* steps_out,
+                                                             unsigned long long* chain, const DCard* cards, const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  stage_cards(s_cards, cards);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G g;
+  init_g(g, s_cards, wt);
+  SbState s;
+  load_state(s, states + (size_t)i * SB_STATE_BYTES);
+  unpack(g, s);
+  unsigned long long ch = DIGEST ? chain[i] : 0ull;
+  int k = 0;
+  while (!(g.done & SB_DONE) && !g.err && k < max_steps) {
+    u32 m[SB_MASK_WORDS];
+    int nl = legal_mask(g, m);
+    int pick = (int)agent_pick(g.seed_lo, g.seed_hi, g.steps, (u32)nl);
+    int a = 0;
+    for (int w = 0; w < SB_MASK_WORDS; w++) {  // pick-th set bit
+      int c = __popc(m[w]);
+      if (pick < c) { u32 v = m[w]; for (int q = 0; q < pick; q++) v &= v - 1; a = w * 32 + __ffs(v) - 1; break; }
+      pick -= c;
+    }
+    game_step(g, a);
+    compact(g);
+    if (DIGEST) { pack(g, s); ch = (ch ^ digest_state(s)) * 0x100000001B3ull; }
+    k++;
+  }
+  pack(g, s);
+  store_state(states + (size_t)i * SB_STATE_BYTES, s);
+  if (steps_out) steps_out[i] = k;
+  if (DIGEST) chain[i] = ch;
+}
+
+// ---------------------------------------------------------------- warp-per-game kernels (heuristic agent)
+struct Best { double score; int action; };
+SBD_FI Best warp_argmax(Best b) {  // np.argmax: first maximum = lowest action id among equal scores
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    double os = __shfl_xor_sync(0xFFFFFFFFu, b.score, off);
+    int oa = __shfl_xor_sync(0xFFFFFFFFu, b.action, off);
+    bool take = oa >= 0 && (b.action < 0 || os > b.score || (os == b.score && oa < b.action));
+    if (take) { b.score = os; b.action = oa; }
+  }
+  return b;
+}
+SBD_FI double score_delta(const double* w, const double* fc, const double* fn) {  // evo/heuristic_agent.py:23-51,82-122
+  double d = 0.0;
+#pragma unroll
+  for (int i = 0; i < SB_N_FEATURES; i++) d = __dadd_rn(d, __dmul_rn(w[i], __dsub_rn(fn[i], fc[i])));
+  double eff = __dsub_rn(fn[0], fc[0]);
+  double rp = eff < -0.3 ? __dmul_rn(fabs(eff), 0.2) : 0.0;
+  return __dsub_rn(__dsub_rn(-d, d), rp);
+}
+// One decision for the game whose packed base state sits in shared memory.  Every lane forks the base,
+// applies its candidate(s), scores them; returns the warp-wide best action.  If `commit`, the lane that
+// owns the winner leaves the post-action state packed in `base` (the fork becomes the game).
+SBD_NI int decide(G& g, SbState* base, const double* w, double* scores_out, bool commit) {
+  const int lane = threadIdx.x & 31;
+  unpack(g, *base);
+  u32 m[SB_MASK_WORDS];
+  legal_mask(g, m);
+  double fc[SB_N_FEATURES], fn[SB_N_FEATURES];
+  const int cur_err = features(g, fc);
+  Best best; best.score = 0.0; best.action = -1;
+  int k = 0, last = -1;
+  bool dirty = false;
+  for (int a = 0; a < SB_N_ACTIONS; a++) {
+    if (!(m[a >> 5] >> (a & 31) & 1)) continue;
+    if ((k++ & 31) != lane) continue;
+    if (dirty) unpack(g, *base);
+    game_step(g, a);
+    dirty = true; last = a;
+    double sc = 0.0;
+    int nerr = g.err;
+    if (!nerr) nerr = features(g, fn);
+    if (!nerr && !cur_err) sc = score_delta(w, fc, fn);
+    if (scores_out) scores_out[a] = sc;
+    if (best.action < 0 || sc > best.score) { best.score = sc; best.action = a; }
+  }
+  Best win = warp_argmax(best);
+  int action = win.action < 0 ? SB_ACTION_PASS : win.action;
+  if (commit) {
+    __syncwarp();  // everybody is done reading the base
+    bool owner = (win.action >= 0) ? (best.action == win.action) : (lane == 0);
+    if (owner) {
+      if (last != action) { unpack(g, *base); game_step(g, action); }
+      pack(g, *base);
+    }
+    __syncwarp();
+  }
+  return action;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select_action(int n, const u8* states, const double* weights, u8* actions,
+                                                                      double* scores, const DCard* cards, const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  __shared__ __align__(16) SbState s_base[WARPS_PER_CTA];
+  stage_cards(s_cards, cards);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gi = blockIdx.x * WARPS_PER_CTA + warp;
+  if (gi >= n) return;
+  reinterpret_cast<uint4*>(&s_base[warp])[lane] = reinterpret_cast<const uint4*>(states + (size_t)gi * SB_STATE_BYTES)[lane];
+  __syncwarp();
+  if (scores) for (int a = lane; a < SB_N_ACTIONS; a += 32) scores[(size_t)gi * SB_N_ACTIONS + a] = __longlong_as_double(0x7FF8000000000000ll);
+  __syncwarp();
+  G g;
+  init_g(g, s_cards, wt);
+  double w[SB_N_FEATURES];
+  for (int k = 0; k < SB_N_FEATURES; k++) w[k] = weights[(size_t)gi * SB_N_FEATURES + k];
+  int a = decide(g, &s_base[warp], w, scores ? scores + (size_t)gi * SB_N_ACTIONS : nullptr, false);
+  if (lane == 0) actions[gi] = (u8)a;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rollout_heuristic(int n, u8* states, const double* w_first, const double* w_second,
+                                                                          const int* idx_first, const int* idx_second, int max_steps,
+                                                                          i8* result, int* steps_out, const DCard* cards, const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  __shared__ __align__(16) SbState s_base[WARPS_PER_CTA];
+  stage_cards(s_cards, cards);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gi = blockIdx.x * WARPS_PER_CTA + warp;
+  if (gi >= n) return;
+  SbState* base = &s_base[warp];
+  reinterpret_cast<uint4*>(base)[lane] = reinterpret_cast<const uint4*>(states + (size_t)gi * SB_STATE_BYTES)[lane];
+  __syncwarp();
+  G g;
+  init_g(g, s_cards, wt);
+  double wf[SB_N_FEATURES], ws[SB_N_FEATURES];
+  const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
+  const double* ps = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
+  for (int k = 0; k < SB_N_FEATURES; k++) { wf[k] = pf[k]; ws[k] = ps[k]; }
+  int k = 0, res = -1;
+  while (k < max_steps) {
+    if (base->pl[0].base < 0 || base->pl[1].base < 0) break;
+    decide(g, base, base->player_sign == 1 ? wf : ws, nullptr, true);
+    k++;
+    if (base->err) { res = -2; break; }
+  }
+  if (res != -2) {
+    bool l0 = base->pl[0].base < 0, l1 = base->pl[1].base < 0;
+    res = (l1 && !l0) ? 0 : (l0 && !l1) ? 1 : -1;
+  }
+  __syncwarp();
+  reinterpret_cast<uint4*>(states + (size_t)gi * SB_STATE_BYTES)[lane] = reinterpret_cast<const uint4*>(base)[lane];
+  if (lane == 0) { if (result) result[gi] = (i8)res; if (steps_out) steps_out[gi] = k; }
+}
+
+__global__ void k_accumulate_fitness(int n, const i8* result, const int* idx_first, int* counts) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ind = idx_first ? idx_first[i] : i;
+  int r = result[i];
+  atomicAdd(&counts[ind * 3 + (r == 0 ? 0 : r == 1 ? 2 : 1)], 1);
+}
+
+// ================================================================ host side / C ABI
+struct HostCard {
+  int kind, faction, cost, strength, movement, trigger, fixed, has_ability, first_type, types, obs_id;
+  int has_target, t_kind, t_side, t_types, t_xtypes, t_status, t_xstatus, t_limit, t_nonhero, t_base;
+  int p[4];
+};
+static const HostCard HOST_CARDS[SBC_COUNT] = {
+#include "sb_card_table.inc"
+};
+
+struct SbHandle {
+  int device;
+  int sm_count;
+  DCard* d_cards;
+  double* d_wt;
+  unsigned long long launches;
+  char err[256];
+  // staging for the *_host entry points
+  u8* d_stage; size_t stage_bytes;
+  cudaStream_t stream;
+};
+
+static int fail(SbHandle* h, cudaError_t e, const char* what) {
+  if (h) snprintf(h->err, sizeof h->err, "%s: %s", what, cudaGetErrorString(e));
+  return -(int)e;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, e_, #call); } while (0)
+#define LAUNCH_CHECK() do { h->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(h, e_, "kernel launch"); } while (0)
+
+extern "C" {
+
+int sb_abi_version(void) { return SB_ABI_VERSION; }
+int sb_state_bytes(void) { return (int)sizeof(SbState); }
+int sb_card_count(void) { return SBC_COUNT; }
+int sb_card_info(int card, int32_t out[12]) {
+  if (card < 0 || card >= SBC_COUNT) return -1;
+  const HostCard& c = HOST_CARDS[card];
+  const int v[12] = {c.kind, c.faction, c.cost, c.strength, c.movement, c.trigger, c.fixed, c.has_ability, c.first_type, c.types, c.obs_id, c.has_target};
+  for (int i = 0; i < 12; i++) out[i] = v[i];
+  return 0;
+}
+
+int sb_create(int device, SbHandle** out) {
+  *out = nullptr;
+  SbHandle* h = (SbHandle*)calloc(1, sizeof(SbHandle));
+  if (!h) return -2;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0 || device >= count) { free(h); return e != cudaSuccess ? -(int)e : -(int)cudaErrorNoDevice; }
+  h->device = device;
+  *out = h;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  h->sm_count = prop.multiProcessorCount;
+  // the rules engine recurses (ability -> damage -> death trigger -> ability ...): size the per-thread stack
+  CK(cudaDeviceSetLimit(cudaLimitStackSize, 48 * 1024));
+  DCard tab[SBC_COUNT];
+  memset(tab, 0, sizeof tab);
+  for (int i = 0; i < SBC_COUNT; i++) {
+    const HostCard& c = HOST_CARDS[i];
+    DCard& d = tab[i];
+    d.kind = (u8)c.kind; d.cost = (i8)c.cost; d.strength = (i8)c.strength; d.movement = (u8)c.movement; d.trigger = (u8)c.trigger;
+    d.flags = (u8)((c.fixed ? DCF_FIXED : 0) | (c.has_ability ? DCF_ABILITY : 0) | (c.has_target ? DCF_TARGET : 0) |
+                   (c.t_base ? DCF_TBASE : 0) | (c.t_nonhero ? DCF_TNONHERO : 0));
+    d.first_type = (u8)c.first_type; d.t_ks = (u8)(c.t_kind | (c.t_side << 2));
+    d.types = (u16)c.types; d.obs_id = (i16)c.obs_id; d.t_types = (u16)c.t_types; d.t_xtypes = (u16)c.t_xtypes;
+    d.t_status = (u8)c.t_status; d.t_xstatus = (u8)c.t_xstatus; d.t_limit = (i8)c.t_limit;
+    for (int k = 0; k < 4; k++) d.p[k] = (i8)c.p[k];
+  }
+  CK(cudaMalloc(&h->d_cards, sizeof tab));
+  CK(cudaMemcpy(h->d_cards, tab, sizeof tab, cudaMemcpyHostToDevice));
+  static double wt[WT_N];
+  volatile double w = 1.0;  // player.py:32,59: w*1.6+100 with two roundings (volatile blocks FMA contraction)
+  for (int i = 0; i < WT_N; i++) { wt[i] = w; volatile double m = w * 1.6; w = m + 100.0; }
+  CK(cudaMalloc(&h->d_wt, sizeof wt));
+  CK(cudaMemcpy(h->d_wt, wt, sizeof wt, cudaMemcpyHostToDevice));
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  return 0;
+}
+int sb_destroy(SbHandle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  if (h->d_cards) cudaFree(h->d_cards);
+  if (h->d_wt) cudaFree(h->d_wt);
+  if (h->d_stage) cudaFree(h->d_stage);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  free(h);
+  return 0;
+}
+const char* sb_last_error(SbHandle* h) { return h ? h->err : "null handle"; }
+int sb_device(SbHandle* h) { return h->device; }
+int sb_sm_count(SbHandle* h) { return h->sm_count; }
+uint64_t sb_launch_count(SbHandle* h) { return h->launches; }
+
+static inline int grid_for(int n, int per_cta) { return (n + per_cta - 1) / per_cta; }
+
+int sb_reset(SbHandle* h, int n, const uint64_t* seeds_d, const uint8_t* decks_d, int n_deck, int decks_shared,
+             const uint8_t* factions_d, uint8_t* states_d, void* stream) {
+  if (n <= 0) return 0;
+  k_reset<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, (const unsigned long long*)seeds_d, decks_d, n_deck,
+                                                                        decks_shared, factions_d, states_d, h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_legal_mask(SbHandle* h, int n, const uint8_t* states_d, uint32_t* masks_d, void* stream) {
+  if (n <= 0) return 0;
+  k_legal_mask<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, masks_d, h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_step(SbHandle* h, int n, uint8_t* states_d, const uint8_t* actions_d, int8_t* reward_d, uint8_t* done_d, uint8_t* err_d,
+            uint32_t* next_masks_d, void* stream) {
+  if (n <= 0) return 0;
+  k_step<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, actions_d, (i8*)reward_d, done_d, err_d, next_masks_d,
+                                                                       h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_observe(SbHandle* h, int n, const uint8_t* states_d, int32_t* obs_d, uint8_t* err_d, void* stream) {
+  if (n <= 0) return 0;
+  k_observe<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, obs_d, err_d, h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_features(SbHandle* h, int n, const uint8_t* states_d, double* feat_d, uint8_t* err_d, void* stream) {
+  if (n <= 0) return 0;
+  k_features<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, feat_d, err_d, h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_select_action(SbHandle* h, int n, const uint8_t* states_d, const double* weights_d, uint8_t* actions_d, double* scores_d,
+                     void* stream) {
+  if (n <= 0) return 0;
+  k_select_action<<<grid_for(n, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(n, states_d, weights_d, actions_d, scores_d,
+                                                                                                h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max_steps, int32_t* steps_d, uint64_t* chain_d, void* stream) {
+  if (n <= 0) return 0;
+  if (chain_d)
+    k_rollout_random<true><<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, max_steps, steps_d,
+                                                                                         (unsigned long long*)chain_d, h->d_cards, h->d_wt);
+  else
+    k_rollout_random<false><<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, max_steps, steps_d, nullptr,
+                                                                                          h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_first_d, const double* w_second_d,
+                         const int32_t* idx_first_d, const int32_t* idx_second_d, int max_steps, int8_t* result_d, int32_t* steps_d,
+                         void* stream) {
+  if (n <= 0) return 0;
+  k_rollout_heuristic<<<grid_for(n, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+      n, states_d, w_first_d, w_second_d, idx_first_d, idx_second_d, max_steps, (i8*)result_d, steps_d, h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_accumulate_fitness(SbHandle* h, int n, const int8_t* result_d, const int32_t* idx_first_d, int32_t* counts_d, void* stream) {
+  if (n <= 0) return 0;
+  k_accumulate_fitness<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, (const i8*)result_d, idx_first_d, counts_d);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------- host-buffer (e2e) variants
+static int ensure_stage(SbHandle* h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return 0;
+  if (h->d_stage) cudaFree(h->d_stage);
+  h->d_stage = nullptr; h->stage_bytes = 0;
+  CK(cudaMalloc(&h->d_stage, bytes));
+  h->stage_bytes = bytes;
+  return 0;
+}
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int sb_step_host(SbHandle* h, int n, uint8_t* states, const uint8_t* actions, int8_t* reward, uint8_t* done, uint8_t* err,
+                 uint32_t* next_masks) {
+  if (n <= 0) return 0;
+  size_t o_states = 0, o_act = al256((size_t)n * SB_STATE_BYTES), o_rew = o_act + al256(n), o_done = o_rew + al256(n),
+         o_err = o_done + al256(n), o_mask = o_err + al256(n), total = o_mask + al256((size_t)n * SB_MASK_WORDS * 4);
+  int rc = ensure_stage(h, total);
+  if (rc) return rc;
+  u8* d = h->d_stage;
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(d + o_states, states, (size_t)n * SB_STATE_BYTES, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_act, actions, n, cudaMemcpyHostToDevice, st));
+  rc = sb_step(h, n, d + o_states, d + o_act, (int8_t*)(d + o_rew), d + o_done, d + o_err, next_masks ? (uint32_t*)(d + o_mask) : nullptr, st);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(states, d + o_states, (size_t)n * SB_STATE_BYTES, cudaMemcpyDeviceToHost, st));
+  if (reward) CK(cudaMemcpyAsync(reward, d + o_rew, n, cudaMemcpyDeviceToHost, st));
+  if (done) CK(cudaMemcpyAsync(done, d + o_done, n, cudaMemcpyDeviceToHost, st));
+  if (err) CK(cudaMemcpyAsync(err, d + o_err, n, cudaMemcpyDeviceToHost, st));
+  if (next_masks) CK(cudaMemcpyAsync(next_masks, d + o_mask, (size_t)n * SB_MASK_WORDS * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int sb_rollout_random_host(SbHandle* h, int n, const uint64_t* seeds, const uint8_t* decks, int n_deck, const uint8_t* factions,
+                           int max_steps, uint8_t* states_out, int32_t* steps_out, uint64_t* chain_out) {
+  if (n <= 0) return 0;
+  size_t o_states = 0, o_seed = al256((size_t)n * SB_STATE_BYTES), o_deck = o_seed + al256((size_t)n * 8),
+         o_fac = o_deck + al256((size_t)2 * n_deck), o_steps = o_fac + 256, o_chain = o_steps + al256((size_t)n * 4),
+         total = o_chain + al256((size_t)n * 8);
+  int rc = ensure_stage(h, total);
+  if (rc) return rc;
+  u8* d = h->d_stage;
+  cudaStream_t st = h->stream;
+  CK(cudaMemcpyAsync(d + o_seed, seeds, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_deck, decks, (size_t)2 * n_deck, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_fac, factions, 2, cudaMemcpyHostToDevice, st));
+  rc = sb_reset(h, n, (const uint64_t*)(d + o_seed), d + o_deck, n_deck, 1, d + o_fac, d + o_states, st);
+  if (rc) return rc;
+  if (chain_out) CK(cudaMemsetAsync(d + o_chain, 0, (size_t)n * 8, st));
+  rc = sb_rollout_random(h, n, d + o_states, max_steps, (int32_t*)(d + o_steps), chain_out ? (uint64_t*)(d + o_chain) : nullptr, st);
+  if (rc) return rc;
+  if (states_out) CK(cudaMemcpyAsync(states_out, d + o_states, (size_t)n * SB_STATE_BYTES, cudaMemcpyDeviceToHost, st));
+  if (steps_out) CK(cudaMemcpyAsync(steps_out, d + o_steps, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (chain_out) CK(cudaMemcpyAsync(chain_out, d + o_chain, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+"""Batched Stormbound on one B200: device-resident packed states + the kernels of libsb_b200.so.
+
+torch is plumbing only (device memory, streams, torch.distributed); every rule, draw and score is
+computed by the CUDA kernels behind the C ABI (include/sb_b200.h).  No CPU path exists.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._card_table import CARDS
+
+STATE_BYTES = 512
+N_ACTIONS = 156
+MASK_WORDS = 5
+PASS = 155
+
+CARD_INDEX = {c["name"]: i for i, c in enumerate(CARDS)}
+# games/stormbound.py:295-302
+DEFAULT_DECKS = (
+    ["UA07", "U007", "U306", "U061", "B304", "U305", "U320", "U302", "U313", "UA02", "UT32", "U316"],
+    ["UA07", "U007", "U001", "U053", "UE01", "U211", "U206", "U071", "U020", "S013", "B001", "U061"],
+)
+DEFAULT_FACTIONS = (3, 2)  # Faction.IRONCLAD, Faction.SWARM
+
+
+def deck_indices(names):
+    return [CARD_INDEX[n.upper()] for n in names]
+
+
+class Engine:
+    """One handle per device (sb_create).  All tensors passed in must live on that device."""
+
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise _lib.SbError("no CUDA device: the B200 simulator has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        h = ctypes.c_void_p()
+        rc = self.lib.sb_create(self.device.index, ctypes.byref(h))
+        if rc != 0:
+            msg = self.lib.sb_last_error(h).decode() if h else "sb_create failed"
+            raise _lib.SbError("sb_create(%d) -> %d: %s" % (self.device.index, rc, msg))
+        self.h = h
+        torch.cuda.set_device(self.device)  # sb_create sets the stack-size limit on this device's primary context
+        self.sm_count = self.lib.sb_sm_count(h)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc, what):
+        if rc != 0:
+            raise _lib.SbError("%s -> %d: %s" % (what, rc, self.lib.sb_last_error(self.h).decode()))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+    def _dev(self, t, dtype):
+        assert t.device == self.device and t.dtype == dtype and t.is_contiguous(), (t.device, t.dtype)
+        return t
+
+    @property
+    def launches(self):
+        return int(self.lib.sb_launch_count(self.h))
+
+    def empty_states(self, n):
+        return torch.empty((n, STATE_BYTES), dtype=torch.uint8, device=self.device)
+
+    # ------------------------------------------------------------------ C ABI wrappers (device tensors)
+    def reset(self, seeds, decks=None, factions=None, out=None):
+        """seeds: int64/uint64 tensor [n] on device.  decks: None (default decks), [2,k] shared or [n,2,k]."""
+        n = seeds.numel()
+        seeds = self._dev(seeds.view(torch.int64) if seeds.dtype != torch.int64 else seeds, torch.int64)
+        if decks is None:
+            decks = torch.tensor([deck_indices(d) for d in DEFAULT_DECKS], dtype=torch.uint8, device=self.device)
+            factions = torch.tensor(DEFAULT_FACTIONS, dtype=torch.uint8, device=self.device)
+        decks = self._dev(decks, torch.uint8)
+        shared = 1 if decks.dim() == 2 else 0
+        n_deck = decks.shape[-1]
+        if factions is None:
+            factions = torch.zeros((2,) if shared else (n, 2), dtype=torch.uint8, device=self.device)
+        factions = self._dev(factions, torch.uint8)
+        assert (factions.dim() == 1) == bool(shared)
+        states = out if out is not None else self.empty_states(n)
+        self._check(self.lib.sb_reset(self.h, n, self._p(seeds), self._p(decks), n_deck, shared, self._p(factions),
+                                      self._p(states), self._stream()), "sb_reset")
+        return states
+
+    def legal_mask(self, states, out=None):
+        n = states.shape[0]
+        masks = out if out is not None else torch.empty((n, MASK_WORDS), dtype=torch.int32, device=self.device)
+        self._check(self.lib.sb_legal_mask(self.h, n, self._p(states), self._p(masks), self._stream()), "sb_legal_mask")
+        return masks
+
+    def step(self, states, actions, reward=None, done=None, err=None, next_masks=None):
+        n = states.shape[0]
+        actions = self._dev(actions, torch.uint8)
+        reward = reward if reward is not None else torch.empty(n, dtype=torch.int8, device=self.device)
+        done = done if done is not None else torch.empty(n, dtype=torch.uint8, device=self.device)
+        err = err if err is not None else torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.sb_step(self.h, n, self._p(states), self._p(actions), self._p(reward), self._p(done),
+                                     self._p(err), self._p(next_masks), self._stream()), "sb_step")
+        return reward, done, err
+
+    def observe(self, states):
+        n = states.shape[0]
+        obs = torch.empty((n, 27, 5, 4), dtype=torch.int32, device=self.device)
+        err = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.sb_observe(self.h, n, self._p(states), self._p(obs), self._p(err), self._stream()), "sb_observe")
+        return obs, err
+
+    def features(self, states):
+        n = states.shape[0]
+        f = torch.empty((n, 10), dtype=torch.float64, device=self.device)
+        err = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.sb_features(self.h, n, self._p(states), self._p(f), self._p(err), self._stream()), "sb_features")
+        return f, err
+
+    def select_action(self, states, weights, want_scores=False):
+        n = states.shape[0]
+        weights = self._dev(weights, torch.float64)
+        assert weights.shape == (n, 10)
+        actions = torch.empty(n, dtype=torch.uint8, device=self.device)
+        scores = torch.empty((n, N_ACTIONS), dtype=torch.float64, device=self.device) if want_scores else None
+        self._check(self.lib.sb_select_action(self.h, n, self._p(states), self._p(weights), self._p(actions),
+                                              self._p(scores), self._stream()), "sb_select_action")
+        return actions, scores
+
+    def rollout_random(self, states, max_steps=400, chain=None):
+        n = states.shape[0]
+        steps = torch.empty(n, dtype=torch.int32, device=self.device)
+        self._check(self.lib.sb_rollout_random(self.h, n, self._p(states), max_steps, self._p(steps), self._p(chain),
+                                               self._stream()), "sb_rollout_random")
+        return steps
+
+    def rollout_heuristic(self, states, w_first, w_second, idx_first=None, idx_second=None, max_steps=400):
+        n = states.shape[0]
+        w_first = self._dev(w_first, torch.float64)
+        w_second = self._dev(w_second, torch.float64)
+        result = torch.empty(n, dtype=torch.int8, device=self.device)
+        steps = torch.empty(n, dtype=torch.int32, device=self.device)
+        self._check(self.lib.sb_rollout_heuristic(self.h, n, self._p(states), self._p(w_first), self._p(w_second),
+                                                  self._p(idx_first), self._p(idx_second), max_steps, self._p(result),
+                                                  self._p(steps), self._stream()), "sb_rollout_heuristic")
+        return result, steps
+
+    def accumulate_fitness(self, result, idx_first, counts):
+        n = result.shape[0]
+        self._check(self.lib.sb_accumulate_fitness(self.h, n, self._p(result), self._p(idx_first), self._p(counts),
+                                                   self._stream()), "sb_accumulate_fitness")
+        return counts
+
+    # ------------------------------------------------------------------ host-buffer (e2e) entry points
+    def step_host(self, states_np, actions_np, want_masks=True):
+        """numpy in, numpy out; H2D + kernel + D2H inside the call (sb_step_host)."""
+        n = states_np.shape[0]
+        reward = np.empty(n, dtype=np.int8)
+        done = np.empty(n, dtype=np.uint8)
+        err = np.empty(n, dtype=np.uint8)
+        masks = np.empty((n, MASK_WORDS), dtype=np.uint32) if want_masks else None
+        self._check(self.lib.sb_step_host(self.h, n, states_np.ctypes.data, actions_np.ctypes.data, reward.ctypes.data,
+                                          done.ctypes.data, err.ctypes.data, masks.ctypes.data if want_masks else None),
+                    "sb_step_host")
+        return reward, done, err, masks
+
+    def rollout_random_host(self, seeds_np, decks_np=None, factions_np=None, max_steps=400, want_states=True, want_chain=False):
+        n = seeds_np.shape[0]
+        if decks_np is None:
+            decks_np = np.array([deck_indices(d) for d in DEFAULT_DECKS], dtype=np.uint8)
+            factions_np = np.array(DEFAULT_FACTIONS, dtype=np.uint8)
+        seeds_np = np.ascontiguousarray(seeds_np, dtype=np.uint64)
+        states = np.empty((n, STATE_BYTES), dtype=np.uint8) if want_states else None
+        steps = np.empty(n, dtype=np.int32)
+        chain = np.zeros(n, dtype=np.uint64) if want_chain else None
+        self._check(self.lib.sb_rollout_random_host(self.h, n, seeds_np.ctypes.data, decks_np.ctypes.data, decks_np.shape[-1],
+                                                    factions_np.ctypes.data, max_steps,
+                                                    states.ctypes.data if want_states else None, steps.ctypes.data,
+                                                    chain.ctypes.data if want_chain else None), "sb_rollout_random_host")
+        return states, steps, chain
+
+
+_engines = {}
+
+
+def get_engine(device=0):
+    if device not in _engines:
+        _engines[device] = Engine(device)
+    return _engines[device]

@@ -18,7 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("SB_REFERENCE", "/root/reference")
 
-from sb_layout import (STATE_DTYPE, CF_FIXED, CF_SINGLE_USE, PF_LEFTMOST_MOVABLE, PF_REPLACABLE, ST_BITS,
+from sb_layout import (STATE_DTYPE, CF_FIXED, CF_OBJ, CF_SINGLE_USE, PF_LEFTMOST_MOVABLE, PF_REPLACABLE, ST_BITS,
                        TF_FIXED, TF_OWNER, TF_STRUCTURE, weight_table, fnv1a64)  # noqa: E402
 
 M32 = 0xFFFFFFFF
@@ -201,11 +201,18 @@ def _status_word(unit):
     return w
 
 
+class PackOverflow(Exception):
+    """The reference state no longer fits the packed layout (deck > 16 cards, hand > 4, ...)."""
+
+
 def pack_reference(game, steps=0, done=0, err=0):
     """Serialise the reference object graph into one packed 512-byte state."""
     r = ref()
     env = game.env
     b = env.board
+    for pl in (b.local, b.remote):
+        if len(pl.deck) > 16 or len(pl.hand) > 4:
+            raise PackOverflow()
     s = np.zeros((), dtype=STATE_DTYPE)
     s["seed_lo"] = env.random.seed & M32
     s["seed_hi"] = env.random.seed >> 32
@@ -223,6 +230,21 @@ def pack_reference(game, steps=0, done=0, err=0):
     for i, c in enumerate(hist):
         s["hist_card"][i] = card_index(c)
         s["hist_owner"][i] = int(c.player.order)
+    objs = []
+
+    def card_flags(c):
+        f = (CF_FIXED if getattr(c, "fixedly_forward", False) else 0) | (CF_SINGLE_USE if c.is_single_use else 0)
+        if getattr(c, "position", None) is not None:
+            f |= CF_OBJ
+        return f
+
+    def note_obj(c, order, in_deck, i):
+        if getattr(c, "position", None) is None:
+            return
+        on_board = c.position.is_valid and b.board[c.position.y][c.position.x] is c
+        objs.append(((order << 7) | (in_deck << 6) | i, c.position.y * 4 + c.position.x if on_board else 0xFF,
+                     0 if on_board else c.strength))
+
     for pl in (b.local, b.remote):
         p = s["pl"][int(pl.order)]
         p["base"], p["max_mana"], p["mana"] = pl.strength, pl.max_mana, pl.current_mana
@@ -232,14 +254,49 @@ def pack_reference(game, steps=0, done=0, err=0):
         for i, c in enumerate(pl.hand):
             p["hand_card"][i] = card_index(c)
             p["hand_cost"][i] = c.cost
-            p["hand_flags"][i] = (CF_FIXED if getattr(c, "fixedly_forward", False) else 0) | \
-                                 (CF_SINGLE_USE if c.is_single_use else 0)
+            p["hand_flags"][i] = card_flags(c)
         for i, c in enumerate(pl.deck):
             p["deck_card"][i] = card_index(c)
             p["deck_cost"][i] = c.cost
-            p["deck_flags"][i] = (CF_FIXED if getattr(c, "fixedly_forward", False) else 0) | \
-                                 (CF_SINGLE_USE if c.is_single_use else 0)
+            p["deck_flags"][i] = card_flags(c)
             p["deck_wn"][i] = r.wn[float(c.weight)]
+    for o in (0, 1):  # ext serialisation order = hand then deck, FIRST then SECOND (o_pack)
+        pl = b.local if int(b.local.order) == o else b.remote
+        for i, c in enumerate(pl.hand):
+            note_obj(c, o, 0, i)
+        for i, c in enumerate(pl.deck):
+            note_obj(c, o, 1, i)
+    ext = s["ext"]
+    ext[91] = len(objs)
+    for k, (loc, tile, strength) in enumerate(objs[:4]):
+        ext[92 + 4 * k] = loc
+        ext[93 + 4 * k] = tile
+        ext[94 + 4 * k] = strength & 255
+        ext[95 + 4 * k] = (strength >> 8) & 255
+    nmem = 0
+    for y in range(5):
+        for x in range(4):
+            e = b.board[y][x]
+            if e is None or type(e).__name__ != "B005":
+                continue
+            for m in e.ability_remembered:
+                if nmem >= 9:
+                    break
+                is_struct = isinstance(m, r.structure.Structure)
+                base = 1 + 10 * nmem
+                ext[base] = y * 4 + x
+                ext[base + 1] = m.position.y * 4 + m.position.x
+                ext[base + 2] = card_index(m)
+                ext[base + 3] = (TF_OWNER if int(m.player.order) else 0) | (TF_STRUCTURE if is_struct else 0) | \
+                                (TF_FIXED if getattr(m, "fixedly_forward", False) else 0) | \
+                                (8 if getattr(m, "ability_remembered", None) else 0)
+                ext[base + 4] = m.strength & 255
+                ext[base + 5] = (m.strength >> 8) & 255
+                w = 0 if is_struct else _status_word(m)
+                for q in range(4):
+                    ext[base + 6 + q] = (w >> (8 * q)) & 255
+                nmem += 1
+    ext[0] = nmem
     for y in range(5):
         for x in range(4):
             e = b.board[y][x]
@@ -295,7 +352,14 @@ def play_random_game(seed, decks=None, factions=None, max_steps=400, record=True
                 masks.append(legal_mask(legal))
                 break
             step += 1
-            st = pack_reference(game, steps=step, done=(1 if done else 0) | (2 if reward else 0))
+            try:
+                st = pack_reference(game, steps=step, done=(1 if done else 0) | (2 if reward else 0))
+            except PackOverflow:
+                err = 2
+                step -= 1
+                actions.append(a)
+                masks.append(legal_mask(legal))
+                break
             actions.append(a)
             masks.append(legal_mask(legal))
             digests.append(fnv1a64(st.tobytes()))
@@ -303,7 +367,7 @@ def play_random_game(seed, decks=None, factions=None, max_steps=400, record=True
             dones.append(done)
             if record:
                 states.append(st)
-    final = pack_reference(game, steps=step, done=(1 if done else 0))
+    final = None if err == 2 else pack_reference(game, steps=step, done=(1 if done else 0))
     return dict(seed=seed, init=init, actions=np.array(actions, dtype=np.uint8),
                 masks=np.array(masks, dtype=np.uint32).reshape(-1, 5),
                 digests=np.array(digests, dtype=np.uint64), states=states, err=err, final=final,

@@ -41,6 +41,7 @@ PF_LEFTMOST_MOVABLE = 2
 # hand / deck card flags
 CF_FIXED = 1        # Unit.fixedly_forward of the card object (B008 toggles it, cards/b008.py:15-16)
 CF_SINGLE_USE = 2   # Card.is_single_use (cards/ua20.py:31)
+CF_OBJ = 4          # record is a (former) board instance of B305 (cards/b305.py:41-45)
 # tile flags
 TF_OWNER = 1        # order of entity.player
 TF_STRUCTURE = 2

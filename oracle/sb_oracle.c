@@ -521,10 +521,20 @@ void o_teleport(Game *g, int id, int dx, int dy) { /* unit.py:373-382 */
 }
 
 /* ------------------------------------------------------------------ hand / deck (player.py:46-81) */
-static int cards_equal(const CardRec *a, const CardRec *b, int ia, int ib) {
-  /* Unit/Structure __eq__: card_id, player, position (unit.py:25-26, structure.py:18-19); Spell: uuid (card.py:22-23) */
-  if (OCARDS[a->card].kind == KIND_SPELL || OCARDS[b->card].kind == KIND_SPELL) return ia == ib;
-  return a->card == b->card;
+/* list.remove(target): index of the first element that `is` target or == target.
+ * Unit/Structure __eq__: card_id, player, position (unit.py:25-26, structure.py:18-19); Spell: uuid
+ * (card.py:22-23).  A board instance of B305 (SB_CF_OBJ) carries a Point position, a pristine card
+ * None: comparing the two evaluates Point.__eq__(None) -> AttributeError (point.py:7). */
+static int first_equal(Game *g, const CardRec *l, int n, int idx) {
+  const CardRec *t = &l[idx];
+  if (OCARDS[t->card].kind == KIND_SPELL) return idx;
+  for (int i = 0; i < idx && i < n; i++) {
+    if (l[i].card != t->card) continue;
+    int oi = l[i].flags & SB_CF_OBJ, ot = t->flags & SB_CF_OBJ;
+    if (oi != ot) { ERR(g, SB_ERR_NONE_TARGET); return idx; }
+    if (!oi) return i; /* both pristine: None == None */
+  }
+  return idx;
 }
 static void player_draw(Game *g, int order, int amount) { /* player.py:46-52 */
   Ply *p = &g->pl[order];
@@ -541,10 +551,9 @@ static void player_draw(Game *g, int order, int amount) { /* player.py:46-52 */
     if (idx > n - 1) idx = n - 1;
     CardRec c = p->deck[idx];
     c.wn = 0;
-    if (p->n_hand >= SB_HAND_MAX + 2) { ERR(g, SB_ERR_OVERFLOW); return; }
+    if (p->n_hand >= SB_HAND_MAX) { ERR(g, SB_ERR_OVERFLOW); return; }
     p->hand[p->n_hand++] = c;
-    int j = idx;
-    for (int i = 0; i < n; i++) if (cards_equal(&p->deck[i], &p->deck[idx], i, idx)) { j = i; break; }
+    int j = first_equal(g, p->deck, n, idx);
     if (j != idx) p->deck[idx].wn = 0; /* the drawn object stays in the deck (weight 1); an equal one leaves */
     memmove(&p->deck[j], &p->deck[j + 1], sizeof(CardRec) * (n - j - 1));
     p->n_deck--;
@@ -557,8 +566,7 @@ static void player_discard(Game *g, int order, int index) { /* player.py:57-66 *
     if (p->deck[i].wn >= 1023) ERR(g, SB_ERR_OVERFLOW); else p->deck[i].wn++;
   }
   CardRec target = p->hand[index];
-  int j = index;
-  for (int i = 0; i < p->n_hand; i++) if (cards_equal(&p->hand[i], &target, i, index)) { j = i; break; }
+  int j = first_equal(g, p->hand, p->n_hand, index);
   memmove(&p->hand[j], &p->hand[j + 1], sizeof(CardRec) * (p->n_hand - j - 1));
   p->n_hand--;
   if (!(target.flags & SB_CF_SINGLE_USE)) {
@@ -590,7 +598,9 @@ void o_player_play(Game *g, int order, int index, int pos_pt) { /* player.py:68-
     return;
   }
   if (pos_pt < 0 || pos_pt >= 20) { ERR(g, SB_ERR_INDEX); return; }
-  int id = o_new_ent(g, target.card, order, c->strength); /* target.copy(), player.py:74 */
+  int strength = c->strength;
+  if (target.flags & SB_CF_OBJ) strength = target.link >= 0 ? g->e[target.link].strength : target.xstr;
+  int id = o_new_ent(g, target.card, order, strength); /* target.copy(), player.py:74 */
   g->e[id].fixed = (target.flags & SB_CF_FIXED) ? 1 : 0;
   g->e[id].single_use = (target.flags & SB_CF_SINGLE_USE) ? 1 : 0;
   if (c->kind == KIND_UNIT) unit_play(g, id, PTX(pos_pt), PTY(pos_pt));
@@ -728,8 +738,8 @@ void o_unpack(Game *g, const SbState *s) {
     p->base = sp->base; p->max_mana = sp->max_mana; p->mana = sp->mana; p->front_line = sp->front_line;
     p->replacable = !!(sp->flags & SB_PF_REPLACABLE); p->leftmost = !!(sp->flags & SB_PF_LEFTMOST);
     p->faction = sp->faction; p->n_hand = sp->n_hand; p->n_deck = sp->n_deck;
-    for (int i = 0; i < SB_HAND_MAX; i++) { p->hand[i].card = sp->hand_card[i]; p->hand[i].cost = sp->hand_cost[i]; p->hand[i].flags = sp->hand_flags[i]; p->hand[i].wn = 0; }
-    for (int i = 0; i < SB_DECK_MAX; i++) { p->deck[i].card = sp->deck_card[i]; p->deck[i].cost = sp->deck_cost[i]; p->deck[i].flags = sp->deck_flags[i]; p->deck[i].wn = sp->deck_wn[i]; }
+    for (int i = 0; i < SB_HAND_MAX; i++) { p->hand[i].card = sp->hand_card[i]; p->hand[i].cost = sp->hand_cost[i]; p->hand[i].flags = sp->hand_flags[i]; p->hand[i].wn = 0; p->hand[i].xstr = 0; p->hand[i].link = -1; }
+    for (int i = 0; i < SB_DECK_MAX; i++) { p->deck[i].card = sp->deck_card[i]; p->deck[i].cost = sp->deck_cost[i]; p->deck[i].flags = sp->deck_flags[i]; p->deck[i].wn = sp->deck_wn[i]; p->deck[i].xstr = 0; p->deck[i].link = -1; }
   }
   for (int y = 0; y < 5; y++) for (int x = 0; x < 4; x++) {
     const SbTile *t = &s->tile[y * 4 + x];
@@ -741,7 +751,27 @@ void o_unpack(Game *g, const SbState *s) {
     for (int k = 0; k < 5; k++) e->st[k] = (t->status >> (SB_ST_BITS * k)) & ((1 << SB_ST_BITS) - 1);
     o_set(g, x, y, id);
   }
-  memcpy(g->ext, s->ext, SB_EXT_BYTES);
+  /* ext: B005 memories keyed by the B005's current tile, then B305 board-instance card records */
+  const uint8_t *x = s->ext;
+  int nm = x[0];
+  for (int i = 0; i < nm && i < NMEM_PACKED; i++) {
+    const uint8_t *r = x + 1 + 10 * i;
+    Mem *m = &g->mem[g->n_mem++];
+    m->b005 = o_at_pt(g, r[0]);
+    m->pos = r[1]; m->card = r[2];
+    m->owner = (r[3] & SB_TF_OWNER) ? 1 : 0; m->is_struct = !!(r[3] & SB_TF_STRUCTURE); m->fixed = !!(r[3] & SB_TF_FIXED); m->nested = !!(r[3] & 8);
+    m->strength = (int16_t)(r[4] | (r[5] << 8));
+    uint32_t w = r[6] | (r[7] << 8) | (r[8] << 16) | ((uint32_t)r[9] << 24);
+    for (int k = 0; k < 5; k++) m->st[k] = (w >> (SB_ST_BITS * k)) & 63;
+  }
+  int no = x[91];
+  for (int i = 0; i < no && i < NOBJ_PACKED; i++) {
+    const uint8_t *r = x + 92 + 4 * i;
+    Ply *p = &g->pl[r[0] >> 7];
+    CardRec *c = (r[0] & 64) ? &p->deck[r[0] & 63] : &p->hand[r[0] & 63];
+    if (r[1] != 0xFF) c->link = o_at_pt(g, r[1]);
+    else { c->link = -1; c->xstr = (int16_t)(r[2] | (r[3] << 8)); }
+  }
 }
 void o_pack(const Game *g, SbState *s) {
   memset(s, 0, sizeof *s);
@@ -776,7 +806,42 @@ void o_pack(const Game *g, SbState *s) {
     }
     t->status = w;
   }
-  memcpy(s->ext, g->ext, SB_EXT_BYTES);
+  uint8_t *x = s->ext;
+  int nm = 0;
+  for (int tile = 0; tile < 20; tile++) { /* canonical order: temples in tile order, each temple's copies in memory order */
+    int bid = g->board[tile >> 2][tile & 3];
+    if (bid < 0 || g->e[bid].card != SBC_B005) continue;
+    for (int i = 0; i < g->n_mem; i++) {
+      const Mem *m = &g->mem[i];
+      if (m->b005 != bid) continue;
+      if (nm >= NMEM_PACKED) { s->err = s->err ? s->err : SB_ERR_OVERFLOW; break; }
+      uint8_t *r = x + 1 + 10 * nm++;
+      r[0] = (uint8_t)tile; r[1] = (uint8_t)m->pos; r[2] = (uint8_t)m->card;
+      r[3] = (m->owner ? SB_TF_OWNER : 0) | (m->is_struct ? SB_TF_STRUCTURE : 0) | (m->fixed ? SB_TF_FIXED : 0) | (m->nested ? 8 : 0);
+      r[4] = (uint8_t)(m->strength & 255); r[5] = (uint8_t)((m->strength >> 8) & 255);
+      uint32_t w = 0;
+      if (!m->is_struct) for (int k = 0; k < 5; k++) w |= (uint32_t)(m->st[k] > 63 ? 63 : m->st[k]) << (SB_ST_BITS * k);
+      r[6] = w & 255; r[7] = (w >> 8) & 255; r[8] = (w >> 16) & 255; r[9] = (w >> 24) & 255;
+    }
+  }
+  x[0] = (uint8_t)nm;
+  int no = 0;
+  for (int o = 0; o < 2; o++) for (int where = 0; where < 2; where++) {
+    const Ply *p = &g->pl[o];
+    int cnt = where ? p->n_deck : p->n_hand;
+    for (int i = 0; i < cnt; i++) {
+      const CardRec *c = where ? &p->deck[i] : &p->hand[i];
+      if (!(c->flags & SB_CF_OBJ)) continue;
+      if (no >= NOBJ_PACKED) { s->err = s->err ? s->err : SB_ERR_OVERFLOW; break; }
+      uint8_t *r = x + 92 + 4 * no++;
+      r[0] = (uint8_t)((o << 7) | (where << 6) | i);
+      int on_board = c->link >= 0 && g->board[g->e[c->link].y][g->e[c->link].x] == c->link;
+      int str = c->link >= 0 ? g->e[c->link].strength : c->xstr;
+      r[1] = on_board ? (uint8_t)PT(g->e[c->link].x, g->e[c->link].y) : 0xFF;
+      r[2] = on_board ? 0 : (uint8_t)(str & 255); r[3] = on_board ? 0 : (uint8_t)((str >> 8) & 255);
+    }
+  }
+  x[91] = (uint8_t)no;
 }
 
 /* ------------------------------------------------------------------ public (ctypes) entry points */
@@ -802,6 +867,7 @@ void sbo_new_game(SbState *out, uint64_t seed, const uint8_t *deck0, const uint8
     for (int i = 0; i < n_deck; i++) {
       p->deck[i].card = order[i]; p->deck[i].cost = OCARDS[order[i]].cost;
       p->deck[i].flags = OCARDS[order[i]].fixed ? SB_CF_FIXED : 0; p->deck[i].wn = i;
+      p->deck[i].xstr = 0; p->deck[i].link = -1;
     }
     player_fill_hand(g, o);
   }

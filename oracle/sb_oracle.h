@@ -15,10 +15,10 @@
 #include "../include/sb_state.h"
 #include "sb_card_ids.h"
 
-#define MAXE 96      /* entity pool per step (on-board + everything created or orphaned this step) */
-#define MAXTRIG 64
+#define MAXE 48      /* entity pool per step (same bound as the CUDA working set) */
+#define MAXTRIG 32
 #define MAXPATH 8
-#define MAXDEPTH 200
+#define MAXDEPTH 60
 
 enum { KIND_UNIT = 0, KIND_STRUCTURE = 1, KIND_SPELL = 2 };
 enum { TR_ON_PLAY = 0, TR_ON_DEATH, TR_BEFORE_ATTACKING, TR_AFTER_ATTACKING, TR_AFTER_SURVIVING,
@@ -58,7 +58,15 @@ typedef struct {  /* unit.py:8-23 / structure.py:8-16 */
   int move_id, resolving_play;
 } Ent;
 
-typedef struct { int card, cost, flags, wn; } CardRec;
+/* xstr/link: only for records that are (former) BOARD INSTANCES of B305 (cards/b305.py:41-45 appends
+ * the board object itself to the hand): link = entity id while that object exists this step, else xstr
+ * is the object's frozen strength.  flags carries SB_CF_OBJ for them. */
+typedef struct { int card, cost, flags, wn, xstr, link; } CardRec;
+/* B005 per-instance memory (cards/b005.py:13,24-33): deep copies of neighbouring friendly entities */
+typedef struct { int b005, pos, card, owner, is_struct, fixed, nested, strength, st[5]; } Mem;  /* nested: the remembered copy was a B005 that itself had memories */
+#define NMEM_W 12
+#define NMEM_PACKED 9
+#define NOBJ_PACKED 4
 
 typedef struct {  /* player.py:13-37 */
   int base, max_mana, mana, front_line, replacable, leftmost, faction;
@@ -77,7 +85,8 @@ typedef struct {
   uint32_t seed_lo, seed_hi, turn, draw;
   int hist_n, hist_card[4], hist_owner[4];
   int depth;
-  uint8_t ext[SB_EXT_BYTES];
+  Mem mem[NMEM_W];
+  int n_mem;
 } Game;
 
 #define ERR(g, code) do { if (!(g)->err) (g)->err = (code); } while (0)

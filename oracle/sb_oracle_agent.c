@@ -14,6 +14,16 @@ uint64_t sbo_digest(const SbState *s);
 
 #define OBS(l, r, c) obs[((l) * 5 + (r)) * 4 + (c)]
 
+/* strength of a (former) board instance of B305 sitting in hand/deck: see CardRec in sb_oracle.h */
+static int obj_strength(const SbState *s, int order, int in_deck, int idx, int dflt) {
+  const uint8_t *x = s->ext;
+  for (int i = 0; i < x[91] && i < NOBJ_PACKED; i++) {
+    const uint8_t *r = x + 92 + 4 * i;
+    if (r[0] == (uint8_t)((order << 7) | (in_deck << 6) | idx))
+      return r[1] != 0xFF ? s->tile[r[1]].strength : (int16_t)(r[2] | (r[3] << 8));
+  }
+  return dflt;
+}
 static void card_row(int32_t *row, int card, int cost, int *err) {
   const OCard *c = &OCARDS[card];
   if (c->obs_id == -32768) *err = SB_ERR_OBS_ID; /* card.py:46 ValueError (Q12) */
@@ -54,7 +64,10 @@ int sbo_observe(const SbState *s, int32_t *obs) {
     }
   }
   const SbPlayer *L = &s->pl[lo], *R = &s->pl[ro];
-  for (int i = 0; i < 4; i++) if (i < L->n_hand) card_row(&OBS(6, i, 0), L->hand_card[i], L->hand_cost[i], &err);
+  for (int i = 0; i < 4; i++) if (i < L->n_hand) {
+    card_row(&OBS(6, i, 0), L->hand_card[i], L->hand_cost[i], &err);
+    if (L->hand_flags[i] & SB_CF_OBJ) OBS(6, i, 2) = obj_strength(s, lo, 0, i, OBS(6, i, 2));
+  }
   for (int c = 0; c < 4; c++) OBS(6, 4, c) = 32767;
   /* deck sorted by (cost, card_id), stable; card index order == card_id order */
   int idx[SB_DECK_MAX];
@@ -68,7 +81,10 @@ int sbo_observe(const SbState *s, int32_t *obs) {
   for (int layer = 0; layer < 6; layer++) {
     for (int k = 0; k < 4; k++) {
       int d = layer * 4 + k;
-      if (d < L->n_deck) card_row(&OBS(7 + layer, k, 0), L->deck_card[idx[d]], L->deck_cost[idx[d]], &err);
+      if (d < L->n_deck) {
+        card_row(&OBS(7 + layer, k, 0), L->deck_card[idx[d]], L->deck_cost[idx[d]], &err);
+        if (L->deck_flags[idx[d]] & SB_CF_OBJ) OBS(7 + layer, k, 2) = obj_strength(s, lo, 1, idx[d], OBS(7 + layer, k, 2));
+      }
     }
     for (int c = 0; c < 4; c++) OBS(7 + layer, 4, c) = 32768;
   }

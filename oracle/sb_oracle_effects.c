@@ -72,9 +72,43 @@ void o_effect(Game *g, int id, int pos_pt, int has_source) {
     for (int i = 0; i < n; i++) { o_deal_damage_pt(g, pts[i], p[0], 1); if (g->err) return; }
     o_destroy(g, id, 1);
     break; }
-  case SBC_B005: /* cards/b005.py -- per-instance memory of deep copies: not modelled (DESIGN.md deviations) */
-    ERR(g, SB_ERR_UNSUPPORTED);
-    break;
+  case SBC_B005: { /* cards/b005.py:15-33.  Deviation: a remembered B005 copy loses ITS OWN memory. */
+    t = T(TK_ANY, TS_FRIENDLY);
+    n = o_surrounding(g, e->x, e->y, CUR(g), &t, pts);
+    int mine = 0;
+    for (int i = 0; i < g->n_mem; i++) if (g->mem[i].b005 == id) mine++;
+    if (mine == 0) {
+      for (int i = 0; i < n; i++) {
+        tid = need(g, pts[i]);
+        if (tid < 0) return;
+        if (g->n_mem >= NMEM_W) { ERR(g, SB_ERR_OVERFLOW); return; }
+        Mem *m = &g->mem[g->n_mem++];
+        const Ent *s = &g->e[tid];
+        m->b005 = id; m->pos = pts[i]; m->card = s->card; m->owner = s->owner; m->is_struct = s->is_struct;
+        m->fixed = s->fixed; m->strength = s->strength; m->nested = 0;
+        if (s->card == SBC_B005) for (int q = 0; q < g->n_mem; q++) if (g->mem[q].b005 == tid) m->nested = 1;
+        for (int k = 0; k < 5; k++) m->st[k] = s->st[k];
+      }
+    } else {
+      int count = 0;
+      for (int i = 0; i < g->n_mem && count < p[0]; i++) {
+        Mem *m = &g->mem[i];
+        if (m->b005 != id) continue;
+        int occ = o_at_pt(g, m->pos);
+        if (occ < 0 || (g->e[occ].is_struct == m->is_struct && g->e[occ].card == m->card && g->e[occ].owner == m->owner)) {
+          int c = o_new_ent(g, m->card, m->owner, m->strength);
+          if (m->nested) { ERR(g, SB_ERR_UNSUPPORTED); return; } /* memories of a remembered temple are not modelled */
+          g->e[c].fixed = m->fixed;
+          for (int k = 0; k < 5; k++) g->e[c].st[k] = m->st[k];
+          o_set(g, PTX(m->pos), PTY(m->pos), c);
+          count++;
+        }
+      }
+      int w = 0;
+      for (int i = 0; i < g->n_mem; i++) if (g->mem[i].b005 != id) g->mem[w++] = g->mem[i];
+      g->n_mem = w;
+    }
+    break; }
   case SBC_B006: { /* cards/b006.py:14-39 */
     t = T(TK_UNIT, TS_FRIENDLY);
     n = o_get_targets(g, CUR(g), &t, PT_NONE, pts);
@@ -171,13 +205,12 @@ void o_effect(Game *g, int id, int pos_pt, int has_source) {
         return;
       }
     }
-    /* first copy: the board instance itself goes to the hand (cost 2); replaying that linked
-     * instance is outside the modelled subset (DESIGN.md deviations) */
+    /* no other temple: the BOARD INSTANCE itself goes to the hand with cost 2 (a live link) */
     {
       Ply *pl = &g->pl[me];
       if (!e->single_use) { if (pl->n_deck == 0) { ERR(g, SB_ERR_INDEX); return; } pl->n_deck--; }
       if (pl->n_hand >= SB_HAND_MAX) { ERR(g, SB_ERR_OVERFLOW); return; }
-      CardRec r = {e->card, p[1], (e->single_use ? SB_CF_SINGLE_USE : 0) | 4, 0};
+      CardRec r = {e->card, p[1], (e->single_use ? SB_CF_SINGLE_USE : 0) | SB_CF_OBJ, 0, 0, id};
       pl->hand[pl->n_hand++] = r;
     }
     break; }
@@ -496,7 +529,7 @@ void o_effect(Game *g, int id, int pos_pt, int has_source) {
       Ply *pl = &g->pl[me];
       int c = cand[o_rng_below(g, 4)];
       if (pl->n_deck >= SB_DECK_MAX) { ERR(g, SB_ERR_OVERFLOW); return; }
-      CardRec r = {c, p[0], SB_CF_SINGLE_USE, 0};
+      CardRec r = {c, p[0], SB_CF_SINGLE_USE, 0, 0, -1};
       pl->deck[pl->n_deck++] = r;
     }
     break; }
