@@ -1,0 +1,237 @@
+#!/usr/bin/env python3
+"""bench.py -- env-steps/s and games/s of the batched Stormbound hot path on N B200s.
+
+Workload (BASELINE.json configs[1]): 4,096 parallel games per GPU, uniform-random legal agents,
+default decks, every game played to completion (max 400 env steps).  One bench "step" = one pass:
+sb_reset (new seeds) + sb_rollout_random over the 4,096 games of each rank.  Weak scaling: every rank
+plays its own 4,096 games (disjoint seeds), no data-path collective.
+
+  python bench.py --gpus 1 --steps 20 --warmup 3
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+  python bench.py --impl reference ...     # CPU arm: the oracle port on all host threads
+
+JSON keys follow the driver contract; `roofline` and `cpu_baseline` are described in DESIGN.md.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT]
+
+B_STEP = 2 * 512 + 1 + 20 + 2  # algorithmic bytes per env step: state in+out, action, mask, reward/done
+METRIC = "env_steps_per_sec"
+WORKLOAD = "4096 parallel games/GPU, uniform-random legal agents, default decks, played to completion (max 400 steps)"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_port(n_games, threads, seed0=10_000_000):
+    """The oracle port (plain C restatement of the reference engine) on `threads` host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import sb_oracle as oracle
+    from monsoon_b200.engine import DEFAULT_DECKS, DEFAULT_FACTIONS, deck_indices
+    d0, d1 = (deck_indices(d) for d in DEFAULT_DECKS)
+    t0 = time.perf_counter()
+    states = np.stack([oracle.new_game(seed0 + i, d0, d1, *DEFAULT_FACTIONS) for i in range(n_games)])
+    total, _steps = oracle.batch_random(states, 400, threads)
+    dt = time.perf_counter() - t0
+    return total, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference is pure Python and cannot travel to the GPU box; its CPU arm is the
+    oracle port (kind "port"), all host threads, on a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_games = 4096
+    for _ in range(args.warmup):
+        cpu_port(n_games, threads)
+    tot_steps, tot_t = 0, 0.0
+    for k in range(args.steps):
+        s, dt = cpu_port(n_games, threads, seed0=20_000_000 + k * n_games)
+        tot_steps += s
+        tot_t += dt
+    value = tot_steps / tot_t
+    sample = "%d games (default decks, random agents, to completion) per step" % n_games
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "env_steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU arm = oracle port (C restatement of the Python reference), not the Python itself"},
+        "cpu_baseline": {"value": value, "unit": "env_steps/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "games_per_sec": n_games * args.steps / tot_t,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--games", type=int, default=4096, help="parallel games per GPU (the named workload is 4096)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from monsoon_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    eng = Engine(local_rank)
+    dev = eng.device
+    n = args.games
+    warmup = max(args.warmup, 3)
+
+    seeds = torch.empty(n, dtype=torch.int64, device=dev)
+    base = torch.arange(n, dtype=torch.int64, device=dev)
+    states = eng.empty_states(n)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    steps_total = torch.zeros((), dtype=torch.int64, device=dev)
+
+    def one_pass(k, timed):
+        seeds.copy_(base + (rank * 1_000_003 + k) * n)
+        flush.fill_(k & 255)  # L2 flush between timed iterations (outside the event-bracketed region)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        eng.reset(seeds, out=states)
+        e1.record()
+        st = eng.rollout_random(states, max_steps=400)
+        e2.record()
+        if timed:
+            steps_total.add_(st.sum())
+        return e0, e1, e2
+
+    for k in range(warmup):
+        one_pass(k, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    events = [one_pass(warmup + k, True) for k in range(args.steps)]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = eng.launches - launches0
+    sampler.stop_flag = True
+    t_ms = sum(e0.elapsed_time(e2) for e0, _e1, e2 in events)
+    t_roll_ms = sum(e1.elapsed_time(e2) for _e0, e1, e2 in events)
+    tt = torch.tensor([t_ms, t_roll_ms], dtype=torch.float64, device=dev)
+    tot = steps_total.clone()
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    t_ms, t_roll_ms = (float(x) for x in tt.cpu())
+    total_steps = int(tot.cpu())
+    value = total_steps / (t_ms * 1e-3)
+
+    # end to end through the C ABI with HOST buffers (sb_rollout_random_host: H2D seeds/decks, both kernels,
+    # D2H final states + step counts, stream sync), wall clock around the call
+    seeds_h = np.arange(n, dtype=np.uint64)
+    e2e_steps, e2e_t = 0, 0.0
+    for k in range(warmup + args.steps):
+        sh = seeds_h + np.uint64((rank * 1_000_003 + 50_000 + k) * n)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _st, steps_h, _ = eng.rollout_random_host(sh, max_steps=400, want_states=True)
+        dt = time.perf_counter() - t0
+        if k >= warmup:
+            e2e_steps += int(steps_h.sum())
+            e2e_t += dt
+    e2 = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+    es = torch.tensor([e2e_steps], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+        dist.all_reduce(es, op=dist.ReduceOp.SUM)
+    e2e_value = int(es.cpu()) / float(e2.cpu())
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        steps_per_launch = total_steps / world / max(args.steps, 1)
+        achieved = B_STEP * steps_per_launch / (t_roll_ms / args.steps * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": "env_steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "games_per_gpu": n, "l2": "flushed between timed iterations (256 MiB fill)",
+                       "timing": "CUDA events on the launch stream, reset+rollout kernels, max over ranks"},
+            "games_per_sec": n * world * args.steps / (t_ms * 1e-3),
+            "env_steps_per_game": total_steps / (n * world * args.steps),
+            "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "env_steps/s", "h2d_bytes_per_step": n * 8 + 24 + 2,
+                    "d2h_bytes_per_step": n * 512 + n * 4},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "k_rollout_random", "peak_source": peak_src,
+                         "algorithmic_bytes_per_env_step": B_STEP},
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            ng = 32768
+            s, dt = cpu_port(ng, threads)
+            out["cpu_baseline"] = {"value": s / dt, "unit": "env_steps/s", "cores": threads, "kind": "port",
+                                   "sample": "%d games of the same workload (%d env steps) in %.2f s" % (ng, s, dt)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -504,7 +504,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       break; }
     case SBC_UA05: {  // cards/ua05.py:13-19
       i8 sd[2], em[2];
-      int ns = list_offsets(ex, ey, D_SIDE, 2, sd);
+      int ns = side_list(ex, ey, sd);
       int ne = empty_of(g, sd, ns, em);
       for (int k = 0; k < ne; k++) spawn_token_unit(g, me, em[k], p[0], UT_ANCIENT);
       break; }

@@ -235,19 +235,49 @@ SBD_NI int get_targets_region(const G& g, int pov, const Target& t, int exclude_
 SBD_FI int get_targets(const G& g, int pov, const Target& t, int exclude_pt, i8* out) {
   return get_targets_region(g, pov, t, exclude_pt, 0xFFFFFu, true, out);
 }
-SBD_FI u32 mask_offsets(int x, int y, const i8* d, int nd) {
+// Neighbourhoods as arithmetic (no lookup tables): masks for the filtered queries, ordered lists for the
+// unfiltered ones.  Orders follow board.py:236-296: side [L,R]; bordering [L,R,y-1,y+1];
+// surrounding [L, L y-1, L y+1, R, R y-1, R y+1, y-1, y+1].
+SBD_FI u32 border_mask(int x, int y) {
   u32 m = 0;
-  for (int i = 0; i < nd; i++) { int xx = x + d[2 * i], yy = y + d[2 * i + 1]; if (valid_xy(xx, yy)) m |= 1u << PT(xx, yy); }
+  if (x > 0) m |= 1u << (y * 4 + x - 1);
+  if (x < 3) m |= 1u << (y * 4 + x + 1);
+  if (y > 0) m |= 1u << (y * 4 + x - 4);
+  if (y < 4) m |= 1u << (y * 4 + x + 4);
   return m;
 }
-SBD_FI int list_offsets(int x, int y, const i8* d, int nd, i8* out) {
+SBD_FI u32 surround_mask(int x, int y) {
+  u32 row = (x > 0 ? 1u << (x - 1) : 0u) | (1u << x) | (x < 3 ? 1u << (x + 1) : 0u);  // columns x-1..x+1
+  u32 m = (row & ~(1u << x)) << (y * 4);
+  if (y > 0) m |= row << (y * 4 - 4);
+  if (y < 4) m |= row << (y * 4 + 4);
+  return m;
+}
+SBD_FI int side_list(int x, int y, i8* out) {
   int n = 0;
-  for (int i = 0; i < nd; i++) { int xx = x + d[2 * i], yy = y + d[2 * i + 1]; if (valid_xy(xx, yy)) out[n++] = (i8)PT(xx, yy); }
+  if (x > 0) out[n++] = (i8)(y * 4 + x - 1);
+  if (x < 3) out[n++] = (i8)(y * 4 + x + 1);
   return n;
 }
-__device__ const i8 D_SIDE[4] = {-1, 0, 1, 0};
-__device__ const i8 D_BORDER[8] = {-1, 0, 1, 0, 0, -1, 0, 1};
-__device__ const i8 D_SURROUND[16] = {-1, 0, -1, -1, -1, 1, 1, 0, 1, -1, 1, 1, 0, -1, 0, 1};
+SBD_FI int border_list(int x, int y, i8* out) {
+  int n = side_list(x, y, out);
+  if (y > 0) out[n++] = (i8)(y * 4 + x - 4);
+  if (y < 4) out[n++] = (i8)(y * 4 + x + 4);
+  return n;
+}
+SBD_FI int surround_list(int x, int y, i8* out) {
+  int n = 0;
+  for (int dx = -1; dx <= 1; dx += 2) {
+    int xx = x + dx;
+    if (xx < 0 || xx > 3) continue;
+    out[n++] = (i8)(y * 4 + xx);
+    if (y > 0) out[n++] = (i8)(y * 4 + xx - 4);
+    if (y < 4) out[n++] = (i8)(y * 4 + xx + 4);
+  }
+  if (y > 0) out[n++] = (i8)(y * 4 + x - 4);
+  if (y < 4) out[n++] = (i8)(y * 4 + x + 4);
+  return n;
+}
 
 SBD_FI void sort_pts_by_y(i8* a, int n, bool desc) {  // stable insertion sort on Point.y (board.py:217,232)
   for (int i = 1; i < n; i++) {
@@ -275,12 +305,12 @@ SBD_NI int column_tiles(const G& g, int x, int y, int pov, const Target* t, bool
   return n;
 }
 SBD_FI int bordering(const G& g, int x, int y, int pov, const Target* t, i8* out) {  // board.py:266-278
-  if (t) return get_targets_region(g, pov, *t, PT_NONE, mask_offsets(x, y, D_BORDER, 4), true, out);
-  return list_offsets(x, y, D_BORDER, 4, out);
+  if (t) return get_targets_region(g, pov, *t, PT_NONE, border_mask(x, y), true, out);
+  return border_list(x, y, out);
 }
 SBD_FI int surrounding(const G& g, int x, int y, int pov, const Target* t, i8* out) {  // board.py:280-296
-  if (t) return get_targets_region(g, pov, *t, PT_NONE, mask_offsets(x, y, D_SURROUND, 8), true, out);
-  return list_offsets(x, y, D_SURROUND, 8, out);
+  if (t) return get_targets_region(g, pov, *t, PT_NONE, surround_mask(x, y), true, out);
+  return surround_list(x, y, out);
 }
 SBD_FI bool within_front_line(const G& g, int order, int y) {  // player.py:96-100 (Q22)
   return order == 0 ? y >= g.pl[order].front_line : y <= g.pl[order].front_line;
@@ -351,7 +381,7 @@ SBD_NI void spell_ability(G& g, int card, int caster, int pos_pt) {
 }
 
 // ---------------------------------------------------------------- status verbs (unit.py:239-275)
-SBD_FI void st_add(G& g, int id, int s) { if (g.e[id].st[s] < 255) g.e[id].st[s]++; }
+SBD_FI void st_add(G& g, int id, int s) { if (g.e[id].st[s] < 255) g.e[id].st[s]++; }  // packed counters saturate at 63 (compact)
 SBD_FI void st_remove(G& g, int id, int s) { if (g.e[id].st[s]) g.e[id].st[s]--; else GERR(g, SB_ERR_INDEX); }
 SBD_FI void v_freeze(G& g, int id) { st_add(g, id, SB_ST_FROZEN); }
 SBD_FI void v_poison(G& g, int id) { if (g.e[id].st[SB_ST_VITALIZED]) st_remove(g, id, SB_ST_VITALIZED); st_add(g, id, SB_ST_POISONED); }
@@ -773,6 +803,7 @@ SBD_NI void compact(G& g) {
     remap[id] = (u8)n;
     tmp[n] = g.e[id];
     tmp[n].path_len = 0; tmp[n].move_id = 0; tmp[n].dmg = 0; tmp[n].fl &= ~(EF_RPLAY | EF_SINGLE);
+    for (int k = 0; k < 5; k++) if (tmp[n].st[k] > 63) tmp[n].st[k] = 63;
     g.board[t] = (i8)n;
     n++;
   }
@@ -796,6 +827,13 @@ SBD_NI void compact(G& g) {
     g.mem[w] = g.mem[i]; g.mem[w].b005 = (i8)r; w++;
   }
   g.n_mem = (u8)w;
+  // what would not fit the packed layout is an overflow there too (keeps rollouts == step-per-launch)
+  int nobj = 0;
+  for (int o = 0; o < 2; o++) {
+    for (int i = 0; i < g.pl[o].n_hand; i++) nobj += (g.pl[o].hand[i].flags & SB_CF_OBJ) != 0;
+    for (int i = 0; i < g.pl[o].n_deck; i++) nobj += (g.pl[o].deck[i].flags & SB_CF_OBJ) != 0;
+  }
+  if (w > NMEM_PACKED || nobj > NOBJ_PACKED) GERR(g, SB_ERR_OVERFLOW);
   for (int i = 0; i < n; i++) g.e[i] = tmp[i];
   g.n_ent = (u8)n;
   g.n_trig = 0; g.resolving = 0; g.depth = 0;
