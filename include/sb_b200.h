@@ -33,6 +33,10 @@ int sb_destroy(SbHandle *h);
 const char *sb_last_error(SbHandle *h);
 int sb_device(SbHandle *h);
 int sb_sm_count(SbHandle *h);
+/* tuning knobs for the rollout kernels: "games_per_warp" = 0 (auto by batch size) or 1..32 consecutive lanes
+ * of every warp that carry a game; "lanes_per_game" = 2..32 selects the lane-group shape (working set in
+ * shared memory) instead. */
+int sb_set_option(SbHandle *h, const char *key, int value);
 /* kernels launched through this handle so far (bench.py's gpu_launches) */
 uint64_t sb_launch_count(SbHandle *h);
 

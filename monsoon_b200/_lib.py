@@ -25,6 +25,7 @@ SIGNATURES = {
     "sb_device": (_int, [_vp]),
     "sb_sm_count": (_int, [_vp]),
     "sb_launch_count": (ctypes.c_uint64, [_vp]),
+    "sb_set_option": (_int, [_vp, ctypes.c_char_p, _int]),
     "sb_reset": (_int, [_vp, _int, _vp, _vp, _int, _int, _vp, _vp, _vp]),
     "sb_legal_mask": (_int, [_vp, _int, _vp, _vp, _vp]),
     "sb_step": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

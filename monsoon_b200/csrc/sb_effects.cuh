@@ -207,6 +207,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
         if (pl.n_hand >= SB_HAND_MAX) { GERR(g, SB_ERR_OVERFLOW); return; }
         CardRec r; r.card = e.card; r.cost = p[1]; r.flags = (u8)((single ? SB_CF_SINGLE_USE : 0) | SB_CF_OBJ); r.link = (i8)id; r.wn = 0; r.xstr = 0;
         pl.hand[pl.n_hand++] = r;
+        g.n_obj++;
       }
       break; }
     // ------------------------------------------------------------ units

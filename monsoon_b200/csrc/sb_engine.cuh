@@ -93,6 +93,8 @@ struct G {
   i8 player_sign;
   u8 hist_n, hist_card[4], hist_owner[4];
   u8 n_ent, n_trig, resolving, depth, n_mem;
+  u8 n_obj;   // card records that are board instances of B305 (SB_CF_OBJ); 0 on the fast path
+  u32 occ;    // occupied-tile bitmask, mirrors board[]
   u8 trig[MAXTRIG];  // entity id | has_source << 7
   Mem mem[NMEM];
   const DCard* cards;   // shared-memory copy
@@ -151,27 +153,29 @@ SBD_FI u32 agent_pick(u32 seed_lo, u32 seed_hi, u32 step, u32 n) {
 SBD_FI int opponent_of(const G& g, int order) { return order == 0 ? 1 - g.local_order : g.local_order; }  // player.py:42-44 (Q3)
 SBD_FI int at_xy(const G& g, int x, int y) { return valid_xy(x, y) ? g.board[y * 4 + x] : -1; }
 SBD_FI int at_pt(const G& g, int pt) { return (unsigned)pt < 20u ? g.board[pt] : -1; }
+// g.occ = bitmask of occupied tiles, kept in step with board[] by the three writers below (+ unpack);
+// every board scan walks the set bits only (a board holds ~6 entities, not 20).
 SBD_FI void set_xy(G& g, int x, int y, int id) {
-  g.board[y * 4 + x] = (i8)id;
-  if (id >= 0) { g.e[id].x = (u8)x; g.e[id].y = (u8)y; }
+  const int t = y * 4 + x;
+  g.board[t] = (i8)id;
+  if (id >= 0) { g.e[id].x = (u8)x; g.e[id].y = (u8)y; g.occ |= 1u << t; } else g.occ &= ~(1u << t);
 }
-SBD_FI void clear_at(G& g, const Ent& e) { g.board[e.y * 4 + e.x] = -1; }
+SBD_FI void clear_at(G& g, const Ent& e) { const int t = e.y * 4 + e.x; g.board[t] = -1; g.occ &= ~(1u << t); }
+// next tile of mask m in scan order: ascending (pov == local: y=0..4, x=0..3) or descending (board.py:157-158)
+SBD_FI int next_tile(u32& m, bool ascending) {
+  int t = ascending ? __ffs(m) - 1 : 31 - __clz(m);
+  m &= ~(1u << t);
+  return t;
+}
 SBD_NI void calc_front_line(G& g, int order) {  // board.py:78-92
-  if (order == g.local_order) {
-    int fl = 4;
-    for (int t = 0; t < 20; t++) {
-      int id = g.board[t];
-      if (id >= 0 && ent_owner(g.e[id]) == order) { int y = t >> 2; fl = y > 1 ? y : 1; break; }
-    }
-    g.pl[order].front_line = (i8)fl;
-  } else {
-    int fl = 0;
-    for (int t = 19; t >= 0; t--) {
-      int id = g.board[t];
-      if (id >= 0 && ent_owner(g.e[id]) == order) { int y = t >> 2; fl = y < 3 ? y : 3; break; }
-    }
-    g.pl[order].front_line = (i8)fl;
+  const bool local = order == g.local_order;
+  int fl = local ? 4 : 0;
+  u32 m = g.occ;
+  while (m) {
+    int t = next_tile(m, local);
+    if (ent_owner(g.e[g.board[t]]) == order) { int y = t >> 2; fl = local ? (y > 1 ? y : 1) : (y < 3 ? y : 3); break; }
   }
+  g.pl[order].front_line = (i8)fl;
 }
 
 // ---------------------------------------------------------------- target queries (board.py:147-296)
@@ -217,12 +221,11 @@ SBD_FI bool ent_matches(const G& g, const Ent& e, int pov, const Target& t) {
 SBD_NI int get_targets_region(const G& g, int pov, const Target& t, int exclude_pt, u32 region, bool base_passes, i8* out) {
   int n = 0;
   bool pov_local = (pov == g.local_order);
-  for (int i = 0; i < 20; i++) {
-    int tile = pov_local ? i : 19 - i;  // y=0..4,x=0..3  vs  y=4..0,x=3..0 (board.py:157-158)
-    if (!(region >> tile & 1) || tile == exclude_pt) continue;
-    int id = g.board[tile];
-    if (id < 0) continue;
-    if (ent_matches(g, g.e[id], pov, t)) out[n++] = (i8)tile;
+  u32 m = g.occ & region;
+  if ((unsigned)exclude_pt < 20u) m &= ~(1u << exclude_pt);
+  while (m) {
+    int tile = next_tile(m, pov_local);
+    if (ent_matches(g, g.e[g.board[tile]], pov, t)) out[n++] = (i8)tile;
   }
   if (t.base && base_passes) {
     int friendly = pov_local ? PT_BASE_LOCAL : PT_BASE_REMOTE;
@@ -685,7 +688,9 @@ SBD_NI void board_flip(G& g) {  // board.py:94-115
   g.pl[0].front_line = (i8)(4 - g.pl[0].front_line);
   g.pl[1].front_line = (i8)(4 - g.pl[1].front_line);
   for (int t = 0; t < 10; t++) { i8 a = g.board[t]; g.board[t] = g.board[19 - t]; g.board[19 - t] = a; }
-  for (int t = 0; t < 20; t++) { int id = g.board[t]; if (id >= 0) { g.e[id].x = (u8)(t & 3); g.e[id].y = (u8)(t >> 2); } }
+  g.occ = (__brev(g.occ) >> 12);  // tile t -> 19 - t
+  u32 m = g.occ;
+  while (m) { int t = next_tile(m, true); int id = g.board[t]; g.e[id].x = (u8)(t & 3); g.e[id].y = (u8)(t >> 2); }
 }
 SBD_NI void to_next_turn(G& g) {  // board.py:117-145
   i8 pts[24], ids[24];
@@ -721,9 +726,11 @@ SBD_NI int legal_mask(const G& g, u32* m) {
   int n_play = 0;
 #pragma unroll
   for (int i = 0; i < SB_MASK_WORDS; i++) m[i] = 0;
-  u32 empty16 = 0;  // PLACE ordinals over y=4..1, x=0..3 that are empty and within the front line
-  for (int y = 4; y >= p.front_line && y >= 1; y--)
-    for (int x = 0; x < 4; x++) if (g.board[y * 4 + x] < 0) empty16 |= 1u << ((4 - y) * 4 + x);
+  // PLACE ordinals over y=4..1, x=0..3 that are empty and within the front line: ordinal = (4-y)*4 + x
+  const u32 fr = ~g.occ;
+  u32 empty16 = ((fr >> 16) & 0xFu) | (((fr >> 12) & 0xFu) << 4) | (((fr >> 8) & 0xFu) << 8) | (((fr >> 4) & 0xFu) << 12);
+  const int fl = p.front_line < 1 ? 1 : p.front_line;
+  empty16 &= fl > 4 ? 0u : (0xFFFFu >> ((fl - 1) * 4));
   int n_empty = __popc(empty16);
   for (int ci = 0; ci < p.n_hand; ci++) {
     const DCard& c = CARD(g, p.hand[ci].card);
@@ -792,6 +799,14 @@ SBD_NI void game_step(G& g, int action) {
 }
 
 // Between steps only on-board entities matter: rebuild the pool in tile order (what pack+unpack would do).
+SBD_NI void compact(G& g);
+// Fast path between two steps of an in-kernel rollout: nothing references an off-board entity any more
+// (the trigger stack is empty, no B005 memory, no B305 board-instance records), so the garbage can stay
+// until the pool no longer guarantees the 28 free slots a fresh unpack would give.
+SBD_FI void end_of_step(G& g) {
+  if (g.n_ent > SB_N_TILES || g.n_mem || g.n_obj) compact(g);
+  else { g.n_trig = 0; g.resolving = 0; g.depth = 0; }
+}
 SBD_NI void compact(G& g) {
   u8 remap[MAXE];
   for (int i = 0; i < g.n_ent; i++) remap[i] = 0xFF;
@@ -834,6 +849,7 @@ SBD_NI void compact(G& g) {
     for (int i = 0; i < g.pl[o].n_deck; i++) nobj += (g.pl[o].deck[i].flags & SB_CF_OBJ) != 0;
   }
   if (w > NMEM_PACKED || nobj > NOBJ_PACKED) GERR(g, SB_ERR_OVERFLOW);
+  g.n_obj = (u8)(nobj > 255 ? 255 : nobj);
   for (int i = 0; i < n; i++) g.e[i] = tmp[i];
   g.n_ent = (u8)n;
   g.n_trig = 0; g.resolving = 0; g.depth = 0;

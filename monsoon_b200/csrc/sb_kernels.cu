@@ -143,18 +143,11 @@ __global__ void __launch_bounds__(TPB_GAME) k_features(int n, const u8* states, 
 
 // whole uniform-random rollout in one launch; HBM is touched once on the way in and once on the way out
 template <bool DIGEST>
-__global__ void __launch_bounds__(TPB_GAME) k_rollout_random(int n, u8* states, int max_steps, int* steps_out,
-                                                             unsigned long long* chain, const DCard* cards, const double* wt) {
-  __shared__ DCard s_cards[SBC_COUNT];
-  stage_cards(s_cards, cards);
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  G g;
-  init_g(g, s_cards, wt);
+SBD_FI void rollout_random_body(G& g, u8* state_ptr, int max_steps, int* steps_slot, unsigned long long* chain_slot) {
   SbState s;
-  load_state(s, states + (size_t)i * SB_STATE_BYTES);
+  load_state(s, state_ptr);
   unpack(g, s);
-  unsigned long long ch = DIGEST ? chain[i] : 0ull;
+  unsigned long long ch = DIGEST ? *chain_slot : 0ull;
   int k = 0;
   while (!(g.done & SB_DONE) && !g.err && k < max_steps) {
     u32 m[SB_MASK_WORDS];
@@ -167,14 +160,50 @@ __global__ void __launch_bounds__(TPB_GAME) k_rollout_random(int n, u8* states, 
       pick -= c;
     }
     game_step(g, a);
-    compact(g);
+    end_of_step(g);
     if (DIGEST) { pack(g, s); ch = (ch ^ digest_state(s)) * 0x100000001B3ull; }
     k++;
   }
   pack(g, s);
-  store_state(states + (size_t)i * SB_STATE_BYTES, s);
-  if (steps_out) steps_out[i] = k;
-  if (DIGEST) chain[i] = ch;
+  store_state(state_ptr, s);
+  if (steps_slot) *steps_slot = k;
+  if (DIGEST) *chain_slot = ch;
+}
+// shape A: one game per THREAD, working set in local memory (best when the batch oversubscribes the chip)
+template <bool DIGEST>
+__global__ void __launch_bounds__(TPB_GAME) k_rollout_random(int n, u8* states, int max_steps, int* steps_out,
+                                                             unsigned long long* chain, const DCard* cards, const double* wt,
+                                                             int gpw) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  stage_cards(s_cards, cards);
+  // gpw games per warp on CONSECUTIVE lanes (gpw = 32: plain thread-per-game).  Fewer games per warp =
+  // fewer divergent paths serialised on one scheduler slot; consecutive lanes keep the 32-byte local-memory
+  // sectors of the per-thread working set dense.
+  const int lane = threadIdx.x & 31;
+  const int i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * gpw + lane;
+  if (lane >= gpw || i >= n) return;
+  G g;
+  init_g(g, s_cards, wt);
+  rollout_random_body<DIGEST>(g, states + (size_t)i * SB_STATE_BYTES, max_steps, steps_out ? steps_out + i : nullptr,
+                              DIGEST ? chain + i : nullptr);
+}
+// shape B: one game per group of LPG lanes (leader lane runs the rules, no inter-game divergence inside a
+// warp when LPG == 32), working set in SHARED memory.  Trades lanes for issue slots: with few games
+// (BASELINE configs[1]: 4,096) the chip is latency-bound, so every game gets its own warp scheduler slot.
+template <bool DIGEST, int LPG>
+__global__ void __launch_bounds__(128) k_rollout_random_grp(int n, u8* states, int max_steps, int* steps_out,
+                                                            unsigned long long* chain, const DCard* cards, const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  extern __shared__ __align__(16) unsigned char s_dyn[];  // (128 / LPG) working sets
+  G* s_g = reinterpret_cast<G*>(s_dyn);
+  stage_cards(s_cards, cards);
+  const int slot = threadIdx.x / LPG;
+  const int i = blockIdx.x * (128 / LPG) + slot;
+  if (i >= n || (threadIdx.x % LPG) != 0) return;
+  G& g = s_g[slot];
+  init_g(g, s_cards, wt);
+  rollout_random_body<DIGEST>(g, states + (size_t)i * SB_STATE_BYTES, max_steps, steps_out ? steps_out + i : nullptr,
+                              DIGEST ? chain + i : nullptr);
 }
 
 // ---------------------------------------------------------------- warp-per-game kernels (heuristic agent)
@@ -319,6 +348,8 @@ struct SbHandle {
   // staging for the *_host entry points
   u8* d_stage; size_t stage_bytes;
   cudaStream_t stream;
+  int lpg;  // lanes per game for the rollout kernels (0 or 1 = thread per game)
+  int gpw;  // games per warp for the thread-per-game shape (0 = choose by batch size)
 };
 
 static int fail(SbHandle* h, cudaError_t e, const char* what) {
@@ -327,6 +358,36 @@ static int fail(SbHandle* h, cudaError_t e, const char* what) {
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, e_, #call); } while (0)
 #define LAUNCH_CHECK() do { h->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(h, e_, "kernel launch"); } while (0)
+
+static inline int grid_for(int n, int per_cta) { return (n + per_cta - 1) / per_cta; }
+template <bool DIGEST>
+static void launch_rollout_random(SbHandle* h, int lpg, int n, uint8_t* states_d, int max_steps, int32_t* steps_d, uint64_t* chain_d,
+                                  cudaStream_t st) {
+  unsigned long long* ch = (unsigned long long*)chain_d;
+#define GRP(L)                                                                                                              \
+  do {                                                                                                                      \
+    const int smem = (128 / L) * (int)sizeof(G);                                                                            \
+    cudaFuncSetAttribute(k_rollout_random_grp<DIGEST, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);               \
+    k_rollout_random_grp<DIGEST, L><<<grid_for(n, 128 / L), 128, smem, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt); \
+  } while (0)
+  switch (lpg) {
+    case 32: GRP(32); break;
+    case 16: GRP(16); break;
+    case 8: GRP(8); break;
+    case 4: GRP(4); break;
+    case 2: GRP(2); break;
+    default: {
+      int gpw = h->gpw;
+      if (gpw <= 0 || gpw > 32) {  // auto: spread a small batch over all warp schedulers (4 per SM), at most 32 games per warp
+        gpw = (n + h->sm_count * 16 - 1) / (h->sm_count * 16);
+        gpw = gpw < 4 ? 4 : gpw > 32 ? 32 : gpw;
+      }
+      k_rollout_random<DIGEST><<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards,
+                                                                                     h->d_wt, gpw);
+    }
+  }
+#undef GRP
+}
 
 extern "C" {
 
@@ -377,6 +438,10 @@ int sb_create(int device, SbHandle** out) {
   CK(cudaMalloc(&h->d_wt, sizeof wt));
   CK(cudaMemcpy(h->d_wt, wt, sizeof wt, cudaMemcpyHostToDevice));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  const char* env = getenv("SB_LPG");
+  h->lpg = env ? atoi(env) : 0;
+  env = getenv("SB_GPW");
+  h->gpw = env ? atoi(env) : 0;
   return 0;
 }
 int sb_destroy(SbHandle* h) {
@@ -394,7 +459,6 @@ int sb_device(SbHandle* h) { return h->device; }
 int sb_sm_count(SbHandle* h) { return h->sm_count; }
 uint64_t sb_launch_count(SbHandle* h) { return h->launches; }
 
-static inline int grid_for(int n, int per_cta) { return (n + per_cta - 1) / per_cta; }
 
 int sb_reset(SbHandle* h, int n, const uint64_t* seeds_d, const uint8_t* decks_d, int n_deck, int decks_shared,
              const uint8_t* factions_d, uint8_t* states_d, void* stream) {
@@ -440,14 +504,18 @@ int sb_select_action(SbHandle* h, int n, const uint8_t* states_d, const double* 
 }
 int sb_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max_steps, int32_t* steps_d, uint64_t* chain_d, void* stream) {
   if (n <= 0) return 0;
-  if (chain_d)
-    k_rollout_random<true><<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, max_steps, steps_d,
-                                                                                         (unsigned long long*)chain_d, h->d_cards, h->d_wt);
-  else
-    k_rollout_random<false><<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, max_steps, steps_d, nullptr,
-                                                                                          h->d_cards, h->d_wt);
+  // lanes per game: explicit (sb_set_option / SB_LPG) or by batch size -- a warp per game while the chip has warp slots to spare
+  int lpg = h->lpg;
+  if (lpg <= 0) lpg = 1;
+  if (chain_d) launch_rollout_random<true>(h, lpg, n, states_d, max_steps, steps_d, chain_d, (cudaStream_t)stream);
+  else launch_rollout_random<false>(h, lpg, n, states_d, max_steps, steps_d, nullptr, (cudaStream_t)stream);
   LAUNCH_CHECK();
   return 0;
+}
+int sb_set_option(SbHandle* h, const char* key, int value) {
+  if (!strcmp(key, "lanes_per_game")) { h->lpg = value; return 0; }
+  if (!strcmp(key, "games_per_warp")) { h->gpw = value; return 0; }
+  return -1;
 }
 int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_first_d, const double* w_second_d,
                          const int32_t* idx_first_d, const int32_t* idx_second_d, int max_steps, int8_t* result_d, int32_t* steps_d,

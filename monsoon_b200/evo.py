@@ -1,0 +1,303 @@
+"""Drop-in for the reference's evo hot path: evo/game_adapter.py (StormboundAdapter),
+evo/heuristic_agent.py (HeuristicAgent), evo/weights.py (WeightVector) and the evaluation entry point
+evo/fitness.py (FitnessEvaluator.evaluate_population) -- same names, signatures and return shapes,
+computed by the CUDA kernels.  `train_evolutionary.py` / evo/evolution.py run unchanged on top
+(INTEGRATION.md).
+
+Two semantics are offered for the evaluator:
+  * default: the INTENDED loop of evo/fitness.py:193-206 (play until have_winner or max_turns env steps);
+  * reference_faithful=True: reproduces what the reference actually returns (is_terminal is always True,
+    no game is stepped, the row player is always credited a win -> every fitness is 1.0).
+"""
+import time
+
+import numpy as np
+import torch
+
+from .engine import get_engine
+from .games import EngineError, Game, mask_to_actions
+
+FEATURE_NAMES = ["mana_efficiency", "health_advantage", "board_control", "front_line_advantage", "total_strength",
+                 "unit_count", "structure_count", "threatened_base", "protection_value", "hand_quality"]
+
+
+class WeightVector:
+    """evo/weights.py:12-123 (host-side numpy; the ES operators are row f1 of SURVEY 8(f))."""
+
+    def __init__(self, size):
+        self.weights = np.random.uniform(0, 1, size)
+        self.sigmas = np.full(size, 0.1)
+        self.size = size
+
+    def mutate(self, tau, tau_prime, min_sigma):  # evo/weights.py:20-40
+        global_noise = np.random.normal(0, 1)
+        individual_noise = np.random.normal(0, 1, len(self.sigmas))
+        self.sigmas = np.maximum(self.sigmas * np.exp(tau_prime * global_noise + tau * individual_noise), min_sigma)
+        self.weights = np.clip(self.weights + np.random.normal(0, self.sigmas), 0, 1)
+
+    def copy(self):
+        v = WeightVector(len(self.weights))
+        v.weights, v.sigmas, v.size = self.weights.copy(), self.sigmas.copy(), self.size
+        return v
+
+    def dot_product(self, features):
+        if len(features) != self.size:
+            raise ValueError("Feature vector size %d doesn't match weight vector size %d" % (len(features), self.size))
+        return np.dot(self.weights, features)
+
+    def get_weights(self):
+        return self.weights.copy()
+
+    def distance_to(self, other):
+        return np.linalg.norm(self.weights - other.weights)
+
+
+class StateFeatures:
+    """evo/features.py:9-362 result object: the ten features as attributes + get_feature_vector()."""
+
+    def __init__(self, vector, current_player):
+        self._v = np.asarray(vector, dtype=np.float64)
+        self.current_player = current_player
+        for name, val in zip(FEATURE_NAMES, self._v):
+            setattr(self, name, float(val))
+
+    def get_feature_vector(self):
+        return self._v.copy()
+
+    @staticmethod
+    def get_feature_count():
+        return 10
+
+    @staticmethod
+    def get_feature_names():
+        return list(FEATURE_NAMES)
+
+
+class StormboundAdapter:
+    """evo/game_adapter.py:272-372.  Value semantics: apply_action returns an independent state (incl. the
+    random stream position) and leaves this one untouched."""
+
+    def __init__(self, game, reference_faithful=False):
+        self.game = game
+        self.reference_faithful = reference_faithful
+        self.initial_observation = None
+        self._cached_observation = None
+
+    def clone_state(self):
+        a = StormboundAdapter(self.game.clone(), self.reference_faithful)
+        a._cached_observation = self._cached_observation
+        return a
+
+    def get_legal_actions(self):
+        return self.game.legal_actions()
+
+    def apply_action(self, action):
+        new_state = self.clone_state()
+        observation, _reward, _done = new_state.game.step(action)
+        new_state._cached_observation = observation
+        return new_state
+
+    def extract_features(self):
+        f, err = self.game.eng.features(self.game.state)
+        if int(err[0]):
+            raise EngineError(int(err[0]))
+        return StateFeatures(f[0].cpu().numpy(), self.game.to_play())
+
+    def is_terminal(self):
+        if self.reference_faithful:
+            return True  # `have_winner() is not None` is always True (evo/game_adapter.py:342, Q15)
+        return self.game.env.have_winner()
+
+    def get_result(self):
+        if self.reference_faithful:
+            return 1 if self.game.env.have_winner() else 0  # bool == 0 / == 1 (evo/game_adapter.py:351-357)
+        first, second = self._bases()
+        return 0 if (second < 0 <= first) else 1 if (first < 0 <= second) else -1
+
+    def _bases(self):
+        lo = int(self.game._host()[14])
+        l, r = self.game.env.board.local.strength, self.game.env.board.remote.strength
+        return (l, r) if lo == 0 else (r, l)
+
+    def get_current_player(self):
+        return self.game.to_play()
+
+    def get_observation(self):
+        if self._cached_observation is None:
+            self._cached_observation = self.game.env.get_observation()
+        return self._cached_observation
+
+
+class HeuristicAgent:
+    """evo/heuristic_agent.py:14-127; weights is anything with a `.weights` float64[10] (the reference's
+    WeightVector works unchanged)."""
+
+    def __init__(self, weights, player_idx):
+        self.weights = weights
+        self.player_idx = player_idx
+        self.action_count = 0
+        self.game_count = 0
+
+    def _w(self, eng):
+        return torch.as_tensor(np.asarray(self.weights.weights, dtype=np.float64).reshape(1, 10)).to(eng.device)
+
+    def score_action(self, state, action):
+        eng = state.game.eng
+        _a, scores = eng.select_action(state.game.state, self._w(eng), want_scores=True)
+        s = float(scores[0, int(action)])
+        return 0.0 if np.isnan(s) else s  # evo/heuristic_agent.py:48-51: any failure scores 0.0
+
+    def select_action(self, state):
+        eng = state.game.eng
+        a, _ = eng.select_action(state.game.state, self._w(eng))
+        self.action_count += 1
+        return int(a[0])
+
+    def reset_for_new_game(self):
+        self.action_count = 0
+        self.game_count += 1
+
+    def get_weights(self):
+        return self.weights
+
+    def set_weights(self, weights):
+        self.weights = weights
+
+    def get_player_idx(self):
+        return self.player_idx
+
+
+def game_seed(base_seed, generation, i, j, k):
+    """Deterministic per-game seed (the reference uses OS entropy here, Q16): partition-invariant, so any
+    sharding of the games over ranks gives the same fitness."""
+    x = (int(base_seed) * 0x9E3779B97F4A7C15 + generation * 0xBF58476D1CE4E5B9 + i * 0x94D049BB133111EB + j * 0xD6E8FEB86659FD93 + k) & 0x7FFFFFFFFFFFFFFF
+    x ^= x >> 31
+    return (x * 0x2545F4914F6CDD1D) & 0x7FFFFFFFFFFFFFFF
+
+
+class FitnessEvaluator:
+    """evo/fitness.py:18-259.  evaluate_population(population, generation) -> List[float] in [0, 1].
+
+    All games of a generation are played by sb_reset + sb_rollout_heuristic launches; win/draw/loss counts
+    are reduced on the device (sb_accumulate_fitness) and, when torch.distributed is initialised, summed
+    over ranks with one int32 all-reduce after the weights were broadcast from rank 0.
+    `config` needs .games_per_pairing, .max_turns, .seed (num_workers is ignored: there are no threads)."""
+
+    def __init__(self, config, deck_config=None, reference_faithful=False, device=None, engine=None, chunk_games=262144):
+        self.config = config
+        self.deck_config = deck_config
+        self.reference_faithful = reference_faithful
+        self.total_games = 0
+        self.total_time = 0.0
+        self.hall_of_fame = []
+        self.hall_of_fame_size = 5
+        self.use_hall_of_fame = True
+        self.chunk_games = chunk_games
+        self._eng = engine
+        self._device = device
+        self.last_counts = None
+
+    # -- plumbing
+    def _engine(self):
+        if self._eng is None:
+            dev = self._device
+            if dev is None:
+                dev = torch.cuda.current_device() if torch.cuda.is_available() else 0
+            self._eng = get_engine(dev)
+        return self._eng
+
+    @staticmethod
+    def pairings(n_individuals, n_total):
+        """evo/fitness.py:52-59: ordered pairs, the row player is FIRST, no self-play inside the population."""
+        return [(i, j) for i in range(n_individuals) for j in range(n_total) if not (j < n_individuals and i == j)]
+
+    @staticmethod
+    def shard(n_games, rank, world):
+        """contiguous block of the game index space for this rank."""
+        lo = n_games * rank // world
+        hi = n_games * (rank + 1) // world
+        return lo, hi
+
+    def evaluate_population(self, population, generation=0):
+        n = len(population)
+        all_opponents = list(population)
+        if self.use_hall_of_fame and len(self.hall_of_fame) > 0:
+            all_opponents.extend(self.hall_of_fame)
+        n_total = len(all_opponents)
+        g = int(self.config.games_per_pairing)
+        pairs = self.pairings(n, n_total)
+        start = time.time()
+        if self.reference_faithful or not pairs:
+            # evo/fitness.py:193,217: the loop never runs and `False == 0` credits the row player (Q15)
+            counts = np.zeros((n, 3), dtype=np.int64)
+            for i, _j in pairs:
+                counts[i, 0] += g
+        else:
+            counts = self._play(population, all_opponents, pairs, g, generation)
+        self.last_counts = counts
+        scores = counts[:, 0] * 1.0 + counts[:, 1] * 0.5
+        per_individual = (n_total - 1) * g  # evo/fitness.py:112 (Q20 normalisation kept)
+        fitness = [float(s) / per_individual if per_individual else 0.0 for s in scores]
+        self.total_games += len(pairs) * g
+        self.total_time += time.time() - start
+        self._update_hall_of_fame(population, fitness)
+        return fitness
+
+    def _play(self, population, all_opponents, pairs, g, generation):
+        import torch.distributed as dist
+        eng = self._engine()
+        dev = eng.device
+        dist_on = dist.is_available() and dist.is_initialized()
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist_on else (0, 1)
+        w = torch.as_tensor(np.stack([np.asarray(v.weights, dtype=np.float64) for v in all_opponents])).to(dev)
+        if dist_on:
+            dist.broadcast(w, src=0)  # population weights from rank 0
+        n_games = len(pairs) * g
+        lo, hi = self.shard(n_games, rank, world)
+        pair_arr = np.asarray(pairs, dtype=np.int64)
+        base_seed = int(getattr(self.config, "seed", 0) or 0)
+        max_steps = int(self.config.max_turns)
+        counts = torch.zeros((len(population), 3), dtype=torch.int32, device=dev)
+        for c0 in range(lo, hi, self.chunk_games):
+            c1 = min(hi, c0 + self.chunk_games)
+            gi = np.arange(c0, c1, dtype=np.int64)
+            pi, k = gi // g, gi % g
+            i_idx, j_idx = pair_arr[pi, 0], pair_arr[pi, 1]
+            seeds = np.array([game_seed(base_seed, generation, int(a), int(b), int(c)) for a, b, c in zip(i_idx, j_idx, k)],
+                             dtype=np.int64)
+            idx_first = torch.as_tensor(i_idx.astype(np.int32)).to(dev)
+            idx_second = torch.as_tensor(j_idx.astype(np.int32)).to(dev)
+            states = eng.reset(torch.as_tensor(seeds).to(dev))
+            result, _steps = eng.rollout_heuristic(states, w, w, idx_first, idx_second, max_steps=max_steps)
+            eng.accumulate_fitness(result, idx_first, counts)
+        if dist_on:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)  # integer counts: order-independent, bit-exact
+        return counts.cpu().numpy().astype(np.int64)
+
+    def get_stats(self):
+        return {"total_games": self.total_games, "total_time": self.total_time,
+                "avg_time_per_game": self.total_time / max(self.total_games, 1),
+                "games_per_second": self.total_games / max(self.total_time, 1e-6)}
+
+    def reset_stats(self):
+        self.total_games = 0
+        self.total_time = 0.0
+
+    def _update_hall_of_fame(self, population, fitness):  # evo/fitness.py:247-259
+        pairs = sorted(zip(fitness, range(len(population))), key=lambda x: x[0], reverse=True)
+        self.hall_of_fame = [population[i].copy() for _f, i in pairs[:self.hall_of_fame_size]]
+
+
+def play_game(adapter, agent1, agent2, max_turns=400):
+    """The intended loop of evo/fitness.py:178-228 through the shim objects (API-level use; the batched
+    evaluator does the same thing inside one kernel)."""
+    turn_count = 0
+    while not adapter.game.env.have_winner() and turn_count < max_turns:
+        agent = agent1 if adapter.get_current_player() == 0 else agent2
+        adapter = adapter.apply_action(agent.select_action(adapter))
+        turn_count += 1
+    return adapter, turn_count
+
+
+__all__ = ["WeightVector", "StateFeatures", "StormboundAdapter", "HeuristicAgent", "FitnessEvaluator", "play_game",
+           "game_seed", "mask_to_actions", "Game"]

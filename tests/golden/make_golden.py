@@ -1,0 +1,174 @@
+#!/usr/bin/env python3
+"""Generate the committed golden fixtures FROM THE LIVE REFERENCE (build container only).
+
+  python tests/golden/make_golden.py [--procs 8] [--only tapes,chain,rand,heur]
+
+Every fixture is produced by the UNMODIFIED reference engine (/root/reference) driven through
+oracle/ref_harness.py (injected Philox stream, uniform-random agent stream or the reference's own
+HeuristicAgent), then serialised with pack_reference.  Files:
+
+  default_tapes.npz     48 default-deck games, full per-step record (actions, legal masks, state digests,
+                        initial and final packed states)
+  default_chain_10k.npz seeds 0..9999, default decks: steps, chained per-step digest, final digest, flags
+  randdeck_chain.npz    3000 random 12-card faction decks (generate_random_deck semantics; UP01-03 and S203
+                        excluded): decks, factions, steps, chain, final digest, outcome kind
+  heuristic_decisions.npz  states sampled from reference HeuristicAgent-vs-HeuristicAgent games with the
+                        reference's per-action scores, legal set and chosen action, plus whole-game results
+"""
+import argparse
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [os.path.join(ROOT, "oracle"), ROOT]
+
+FNV_PRIME = 0x100000001B3
+M64 = 0xFFFFFFFFFFFFFFFF
+
+
+def chain_of(digests):
+    ch = 0
+    for d in digests:
+        ch = ((ch ^ int(d)) * FNV_PRIME) & M64
+    return ch
+
+
+def random_decks(seed, exclude=("UP01", "UP02", "UP03", "S203")):
+    import random
+    import ref_harness as h
+    r = h.ref()
+    rng = random.Random(seed)
+    decks, factions = [], []
+    for _ in range(2):
+        f = rng.choice([1, 2, 3, 4])
+        pool = [c["name"] for c in r.table[1:113] if c["faction"] in (0, f) and c["name"] not in exclude]
+        decks.append(rng.sample(pool, 12))
+        factions.append(f)
+    return decks, factions
+
+
+def work_chain(seed):
+    import ref_harness as h
+    t = h.play_random_game(seed, record=False)
+    fin = 0 if t["final"] is None else h.fnv1a64(t["final"].tobytes())
+    return seed, t["n_steps"], chain_of(t["digests"]), fin, t["err"], int(t["done"])
+
+
+def work_rand(seed):
+    import ref_harness as h
+    decks, factions = random_decks(seed)
+    r = h.ref()
+    t = h.play_random_game(seed, decks, factions, record=False)
+    fin = 0 if t["final"] is None else h.fnv1a64(t["final"].tobytes())
+    return (seed, [[r.index[n] for n in d] for d in decks], factions, t["n_steps"], chain_of(t["digests"]), fin, t["err"],
+            int(t["done"]), int(t["actions"][-1]) if len(t["actions"]) else 255)
+
+
+def work_tape(seed):
+    import ref_harness as h
+    t = h.play_random_game(seed, record=True)
+    return seed, t["init"], t["final"], t["actions"], t["masks"], t["digests"]
+
+
+def work_heur(seed):
+    """One reference game HeuristicAgent vs HeuristicAgent through StormboundAdapter (intended loop, Q15 bypassed)."""
+    import ref_harness as h
+    r = h.ref()
+    os.chdir(h.REF)
+    from evo.game_adapter import StormboundAdapter
+    from evo.heuristic_agent import HeuristicAgent
+    from evo.weights import WeightVector
+    w1 = np.random.RandomState(1000 + seed).uniform(0, 1, 10)
+    w2 = np.random.RandomState(2000 + seed).uniform(0, 1, 10)
+    wv1, wv2 = WeightVector(10), WeightVector(10)
+    wv1.weights, wv2.weights = w1.copy(), w2.copy()
+    agents = [HeuristicAgent(wv1, 0), HeuristicAgent(wv2, 1)]
+    game = h.make_game(seed)
+    adapter = StormboundAdapter(game)
+    samples, actions = [], []
+    steps = 0
+    with h.quiet():
+        while not adapter.game.env.have_winner() and steps < 400:
+            cur = adapter.get_current_player()
+            agent = agents[cur]
+            legal = adapter.get_legal_actions()
+            if steps % 7 == 3:  # sample: state, weights, per-action reference scores
+                st = h.pack_reference(adapter.game, steps=steps, done=0)
+                scores = np.full(156, np.nan)
+                for a in legal:
+                    scores[a] = agent.score_action(adapter, a)
+                samples.append((st, (w1, w2)[cur].copy(), h.legal_mask(legal), scores))
+            a = agent.select_action(adapter)
+            if samples and steps % 7 == 3:
+                samples[-1] = samples[-1] + (a,)
+            adapter = adapter.apply_action(a)
+            actions.append(a)
+            steps += 1
+    b = adapter.game.env.board
+    first = b.local if int(b.local.order) == 0 else b.remote
+    second = b.remote if int(b.local.order) == 0 else b.local
+    result = 0 if (second.strength < 0 and first.strength >= 0) else 1 if (first.strength < 0 and second.strength >= 0) else -1
+    final = h.pack_reference(adapter.game, steps=steps, done=0)
+    return seed, w1, w2, np.array(actions, dtype=np.uint8), result, h.fnv1a64(final.tobytes()), samples
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--procs", type=int, default=os.cpu_count())
+    ap.add_argument("--only", default="tapes,chain,rand,heur")
+    ap.add_argument("--n-chain", type=int, default=10000)
+    ap.add_argument("--n-rand", type=int, default=3000)
+    ap.add_argument("--n-heur", type=int, default=24)
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    pool = mp.Pool(args.procs)
+    if "tapes" in only:
+        res = pool.map(work_tape, range(48))
+        np.savez_compressed(os.path.join(HERE, "default_tapes.npz"),
+                            seeds=np.array([r[0] for r in res], dtype=np.uint64),
+                            init=np.stack([np.frombuffer(r[1].tobytes(), dtype=np.uint8) for r in res]),
+                            final=np.stack([np.frombuffer(r[2].tobytes(), dtype=np.uint8) for r in res]),
+                            lengths=np.array([len(r[3]) for r in res], dtype=np.int32),
+                            actions=np.concatenate([r[3] for r in res]),
+                            masks=np.concatenate([r[4] for r in res]),
+                            digests=np.concatenate([r[5] for r in res]))
+        print("default_tapes.npz", len(res))
+    if "chain" in only:
+        res = pool.map(work_chain, range(args.n_chain), chunksize=16)
+        a = np.array(res, dtype=object)
+        np.savez_compressed(os.path.join(HERE, "default_chain_10k.npz"),
+                            seeds=np.array([r[0] for r in res], dtype=np.uint64), steps=np.array([r[1] for r in res], dtype=np.int32),
+                            chain=np.array([r[2] for r in res], dtype=np.uint64), final=np.array([r[3] for r in res], dtype=np.uint64),
+                            err=np.array([r[4] for r in res], dtype=np.uint8), done=np.array([r[5] for r in res], dtype=np.uint8))
+        print("default_chain_10k.npz", len(res), "errs", sum(1 for r in res if r[4]))
+    if "rand" in only:
+        res = pool.map(work_rand, range(100000, 100000 + args.n_rand), chunksize=8)
+        np.savez_compressed(os.path.join(HERE, "randdeck_chain.npz"),
+                            seeds=np.array([r[0] for r in res], dtype=np.uint64), decks=np.array([r[1] for r in res], dtype=np.uint8),
+                            factions=np.array([r[2] for r in res], dtype=np.uint8), steps=np.array([r[3] for r in res], dtype=np.int32),
+                            chain=np.array([r[4] for r in res], dtype=np.uint64), final=np.array([r[5] for r in res], dtype=np.uint64),
+                            err=np.array([r[6] for r in res], dtype=np.uint8), done=np.array([r[7] for r in res], dtype=np.uint8),
+                            last_action=np.array([r[8] for r in res], dtype=np.uint8))
+        print("randdeck_chain.npz", len(res), "ref exceptions", sum(1 for r in res if r[6] == 1), "overflow", sum(1 for r in res if r[6] == 2))
+    if "heur" in only:
+        res = pool.map(work_heur, range(args.n_heur), chunksize=1)
+        samples = [s for r in res for s in r[6] if len(s) == 5]
+        np.savez_compressed(os.path.join(HERE, "heuristic_decisions.npz"),
+                            game_seeds=np.array([r[0] for r in res], dtype=np.uint64),
+                            w_first=np.stack([r[1] for r in res]), w_second=np.stack([r[2] for r in res]),
+                            game_lengths=np.array([len(r[3]) for r in res], dtype=np.int32),
+                            game_actions=np.concatenate([r[3] for r in res]),
+                            game_result=np.array([r[4] for r in res], dtype=np.int8),
+                            game_final=np.array([r[5] for r in res], dtype=np.uint64),
+                            states=np.stack([np.frombuffer(s[0].tobytes(), dtype=np.uint8) for s in samples]),
+                            weights=np.stack([s[1] for s in samples]), masks=np.stack([s[2] for s in samples]),
+                            scores=np.stack([s[3] for s in samples]), chosen=np.array([s[4] for s in samples], dtype=np.uint8))
+        print("heuristic_decisions.npz games", len(res), "samples", len(samples))
+
+
+if __name__ == "__main__":
+    main()
