@@ -204,7 +204,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
         Ply& pl = g.pl[me];
         bool single = (e.fl & EF_SINGLE) != 0;
         if (!single) { if (pl.n_deck == 0) { GERR(g, SB_ERR_INDEX); return; } pl.n_deck--; }
-        if (pl.n_hand >= SB_HAND_MAX) { GERR(g, SB_ERR_OVERFLOW); return; }
+        if (pl.n_hand >= HAND_W) { GERR(g, SB_ERR_OVERFLOW); return; }
         CardRec r; r.card = e.card; r.cost = p[1]; r.flags = (u8)((single ? SB_CF_SINGLE_USE : 0) | SB_CF_OBJ); r.link = (i8)id; r.wn = 0; r.xstr = 0;
         pl.hand[pl.n_hand++] = r;
         g.n_obj++;
@@ -218,12 +218,12 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       break;
     case SBC_U017: {  // cards/u017.py:18-34
       Ply& pl = g.pl[me];
-      i8 cand[SB_HAND_MAX]; int nc = 0;
+      i8 cand[HAND_W]; int nc = 0;
       for (int i = 0; i < pl.n_hand; i++) if (CARD(g, pl.hand[i].card).kind == KIND_SPELL && pl.hand[i].cost <= 8) cand[nc++] = (i8)i;
       if (nc > 0) {
         shuffle(g, cand, nc);
         int remaining = 8, nch = 0;
-        i8 chosen[SB_HAND_MAX];
+        i8 chosen[HAND_W];
         for (int i = 0; i < nc; i++) if (pl.hand[cand[i]].cost <= remaining) { chosen[nch++] = cand[i]; remaining -= pl.hand[cand[i]].cost; }
         for (int i = 0; i < nch; i++) {
           const DCard& c = CARD(g, pl.hand[chosen[i]].card);
@@ -524,7 +524,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
         Ply& pl = g.pl[me];
         int k = rng_below(g, 4);
         int c = k == 0 ? SBC_B005 : k == 1 ? SBC_B006 : k == 2 ? SBC_B203 : SBC_B305;
-        if (pl.n_deck >= SB_DECK_MAX) { GERR(g, SB_ERR_OVERFLOW); return; }
+        if (pl.n_deck >= DECK_W) { GERR(g, SB_ERR_OVERFLOW); return; }
         CardRec r; r.card = (u8)c; r.cost = p[0]; r.flags = SB_CF_SINGLE_USE; r.link = -1; r.wn = 0; r.xstr = 0;
         pl.deck[pl.n_deck++] = r;
       }

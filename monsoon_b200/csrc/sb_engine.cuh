@@ -32,6 +32,8 @@ typedef unsigned int u32;
 #define NMEM_PACKED 9
 #define NOBJ_PACKED 4
 #define WT_N 1024
+#define HAND_W 6
+#define DECK_W 20
 
 enum { KIND_UNIT = 0, KIND_STRUCTURE = 1, KIND_SPELL = 2 };
 enum { TR_ON_PLAY = 0, TR_ON_DEATH, TR_BEFORE_ATTACKING, TR_AFTER_ATTACKING, TR_AFTER_SURVIVING,
@@ -78,8 +80,8 @@ struct Ply {  // player.py:13-37
   i16 base, max_mana, mana;
   i8 front_line;
   u8 replacable, leftmost, n_hand, n_deck, faction;
-  CardRec hand[SB_HAND_MAX];
-  CardRec deck[SB_DECK_MAX];
+  CardRec hand[HAND_W];  // working capacity > packed capacity: a cycle holds 17 deck cards for a moment
+  CardRec deck[DECK_W];
 };
 struct Mem { i8 b005; u8 pos, card, fl; i16 strength; u8 st[5]; u8 pad; };  // cards/b005.py remembered copies
 
@@ -616,7 +618,7 @@ SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + num
     if (n <= 0) { GERR(g, SB_ERR_EMPTY_CHOICE); return; }
     double sum = 0.0;
     for (int i = 0; i < n; i++) sum = __dadd_rn(sum, __ldg(&g.wt[p.deck[i].wn]));
-    double cdf[SB_DECK_MAX];
+    double cdf[DECK_W];
     double acc = 0.0;
     for (int i = 0; i < n; i++) { acc = __dadd_rn(acc, __ddiv_rn(__ldg(&g.wt[p.deck[i].wn]), sum)); cdf[i] = acc; }
     double last = cdf[n - 1];
@@ -626,7 +628,7 @@ SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + num
     if (idx > n - 1) idx = n - 1;
     CardRec c = p.deck[idx];
     c.wn = 0;
-    if (p.n_hand >= SB_HAND_MAX) { GERR(g, SB_ERR_OVERFLOW); return; }
+    if (p.n_hand >= HAND_W) { GERR(g, SB_ERR_OVERFLOW); return; }
     p.hand[p.n_hand++] = c;
     int j = first_equal(g, p.deck, n, idx);
     if (j != idx) p.deck[idx].wn = 0;
@@ -643,7 +645,7 @@ SBD_NI void player_discard(G& g, int order, int index) {  // player.py:57-66
   for (int i = j; i < p.n_hand - 1; i++) p.hand[i] = p.hand[i + 1];
   p.n_hand--;
   if (!(target.flags & SB_CF_SINGLE_USE)) {
-    if (p.n_deck >= SB_DECK_MAX) { GERR(g, SB_ERR_OVERFLOW); return; }
+    if (p.n_deck >= DECK_W) { GERR(g, SB_ERR_OVERFLOW); return; }
     target.wn = 0;
     p.deck[p.n_deck++] = target;
   }
@@ -732,7 +734,7 @@ SBD_NI int legal_mask(const G& g, u32* m) {
   const int fl = p.front_line < 1 ? 1 : p.front_line;
   empty16 &= fl > 4 ? 0u : (0xFFFFu >> ((fl - 1) * 4));
   int n_empty = __popc(empty16);
-  for (int ci = 0; ci < p.n_hand; ci++) {
+  for (int ci = 0; ci < p.n_hand && ci < SB_HAND_MAX; ci++) {
     const DCard& c = CARD(g, p.hand[ci].card);
     if (p.hand[ci].cost > p.mana) continue;
     if (c.kind != KIND_SPELL) {
@@ -752,7 +754,7 @@ SBD_NI int legal_mask(const G& g, u32* m) {
     }
   }
   int n = n_play;
-  if (p.replacable) for (int ci = 0; ci < p.n_hand; ci++) { mask_set(m, 148 + ci); n++; }
+  if (p.replacable) for (int ci = 0; ci < p.n_hand && ci < SB_HAND_MAX; ci++) { mask_set(m, 148 + ci); n++; }
   if (n_play == 0) { mask_set(m, 155); n++; }
   return n;
 }
@@ -804,6 +806,9 @@ SBD_NI void compact(G& g);
 // (the trigger stack is empty, no B005 memory, no B305 board-instance records), so the garbage can stay
 // until the pool no longer guarantees the 28 free slots a fresh unpack would give.
 SBD_FI void end_of_step(G& g) {
+  // what the packed layout cannot hold is an overflow here too (keeps in-kernel rollouts == step-per-launch)
+  if (g.pl[0].n_hand > SB_HAND_MAX || g.pl[1].n_hand > SB_HAND_MAX || g.pl[0].n_deck > SB_DECK_MAX || g.pl[1].n_deck > SB_DECK_MAX)
+    GERR(g, SB_ERR_OVERFLOW);
   if (g.n_ent > SB_N_TILES || g.n_mem || g.n_obj) compact(g);
   else { g.n_trig = 0; g.resolving = 0; g.depth = 0; }
 }

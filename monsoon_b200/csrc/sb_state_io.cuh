@@ -99,6 +99,11 @@ SBD_NI void pack(const G& g, SbState& s) {
     sp.base = p.base; sp.max_mana = p.max_mana; sp.mana = p.mana; sp.front_line = p.front_line;
     sp.flags = (u8)((p.replacable ? SB_PF_REPLACABLE : 0) | (p.leftmost ? SB_PF_LEFTMOST : 0));
     sp.n_hand = p.n_hand; sp.n_deck = p.n_deck; sp.faction = p.faction;
+    if (p.n_hand > SB_HAND_MAX || p.n_deck > SB_DECK_MAX) {  // more than the packed layout holds
+      if (!s.err) s.err = SB_ERR_OVERFLOW;
+      if (p.n_hand > SB_HAND_MAX) sp.n_hand = SB_HAND_MAX;
+      if (p.n_deck > SB_DECK_MAX) sp.n_deck = SB_DECK_MAX;
+    }
     for (int i = 0; i < p.n_hand && i < SB_HAND_MAX; i++) { sp.hand_card[i] = p.hand[i].card; sp.hand_cost[i] = p.hand[i].cost; sp.hand_flags[i] = p.hand[i].flags; }
     for (int i = 0; i < p.n_deck && i < SB_DECK_MAX; i++) { sp.deck_card[i] = p.deck[i].card; sp.deck_cost[i] = p.deck[i].cost; sp.deck_flags[i] = p.deck[i].flags; sp.deck_wn[i] = p.deck[i].wn; }
   }

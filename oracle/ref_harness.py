@@ -367,6 +367,7 @@ def play_random_game(seed, decks=None, factions=None, max_steps=400, record=True
             dones.append(done)
             if record:
                 states.append(st)
+    # NOTE: `final` carries the done bit only (no reward bit); the golden tests mask byte 19 accordingly
     final = None if err == 2 else pack_reference(game, steps=step, done=(1 if done else 0))
     return dict(seed=seed, init=init, actions=np.array(actions, dtype=np.uint8),
                 masks=np.array(masks, dtype=np.uint32).reshape(-1, 5),

@@ -541,7 +541,7 @@ static void player_draw(Game *g, int order, int amount) { /* player.py:46-52 */
   for (int k = 0; k < amount; k++) {
     int n = p->n_deck;
     if (n <= 0) { ERR(g, SB_ERR_EMPTY_CHOICE); return; }
-    double sum = 0.0, cdf[SB_DECK_MAX + 2], acc = 0.0;
+    double sum = 0.0, cdf[DECK_W], acc = 0.0;
     for (int i = 0; i < n; i++) sum = sum + WT[p->deck[i].wn];
     for (int i = 0; i < n; i++) { acc = acc + WT[p->deck[i].wn] / sum; cdf[i] = acc; }
     double last = cdf[n - 1];
@@ -551,7 +551,7 @@ static void player_draw(Game *g, int order, int amount) { /* player.py:46-52 */
     if (idx > n - 1) idx = n - 1;
     CardRec c = p->deck[idx];
     c.wn = 0;
-    if (p->n_hand >= SB_HAND_MAX) { ERR(g, SB_ERR_OVERFLOW); return; }
+    if (p->n_hand >= HAND_W) { ERR(g, SB_ERR_OVERFLOW); return; }
     p->hand[p->n_hand++] = c;
     int j = first_equal(g, p->deck, n, idx);
     if (j != idx) p->deck[idx].wn = 0; /* the drawn object stays in the deck (weight 1); an equal one leaves */
@@ -570,7 +570,7 @@ static void player_discard(Game *g, int order, int index) { /* player.py:57-66 *
   memmove(&p->hand[j], &p->hand[j + 1], sizeof(CardRec) * (p->n_hand - j - 1));
   p->n_hand--;
   if (!(target.flags & SB_CF_SINGLE_USE)) {
-    if (p->n_deck >= SB_DECK_MAX) { ERR(g, SB_ERR_OVERFLOW); return; }
+    if (p->n_deck >= DECK_W) { ERR(g, SB_ERR_OVERFLOW); return; }
     target.wn = 0;
     p->deck[p->n_deck++] = target;
   }
@@ -788,6 +788,11 @@ void o_pack(const Game *g, SbState *s) {
     sp->front_line = (int8_t)p->front_line;
     sp->flags = (p->replacable ? SB_PF_REPLACABLE : 0) | (p->leftmost ? SB_PF_LEFTMOST : 0);
     sp->faction = (uint8_t)p->faction; sp->n_hand = (uint8_t)p->n_hand; sp->n_deck = (uint8_t)p->n_deck;
+    if (p->n_hand > SB_HAND_MAX || p->n_deck > SB_DECK_MAX) { /* more than the packed layout holds */
+      if (!s->err) s->err = SB_ERR_OVERFLOW;
+      if (p->n_hand > SB_HAND_MAX) sp->n_hand = SB_HAND_MAX;
+      if (p->n_deck > SB_DECK_MAX) sp->n_deck = SB_DECK_MAX;
+    }
     for (int i = 0; i < p->n_hand && i < SB_HAND_MAX; i++) { sp->hand_card[i] = (uint8_t)p->hand[i].card; sp->hand_cost[i] = (int8_t)p->hand[i].cost; sp->hand_flags[i] = (uint8_t)p->hand[i].flags; }
     for (int i = 0; i < p->n_deck && i < SB_DECK_MAX; i++) { sp->deck_card[i] = (uint8_t)p->deck[i].card; sp->deck_cost[i] = (int8_t)p->deck[i].cost; sp->deck_flags[i] = (uint8_t)p->deck[i].flags; sp->deck_wn[i] = (uint16_t)p->deck[i].wn; }
   }

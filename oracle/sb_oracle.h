@@ -18,6 +18,8 @@
 #define MAXE 48      /* entity pool per step (same bound as the CUDA working set) */
 #define MAXTRIG 32
 #define MAXPATH 8
+#define HAND_W 6
+#define DECK_W 20
 #define MAXDEPTH 60
 
 enum { KIND_UNIT = 0, KIND_STRUCTURE = 1, KIND_SPELL = 2 };
@@ -71,8 +73,8 @@ typedef struct { int b005, pos, card, owner, is_struct, fixed, nested, strength,
 typedef struct {  /* player.py:13-37 */
   int base, max_mana, mana, front_line, replacable, leftmost, faction;
   int n_hand, n_deck;
-  CardRec hand[SB_HAND_MAX + 2];
-  CardRec deck[SB_DECK_MAX + 2];
+  CardRec hand[HAND_W]; /* working capacity > packed capacity (a cycle holds 17 deck cards for a moment) */
+  CardRec deck[DECK_W];
 } Ply;
 
 typedef struct {

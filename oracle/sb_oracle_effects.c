@@ -209,7 +209,7 @@ void o_effect(Game *g, int id, int pos_pt, int has_source) {
     {
       Ply *pl = &g->pl[me];
       if (!e->single_use) { if (pl->n_deck == 0) { ERR(g, SB_ERR_INDEX); return; } pl->n_deck--; }
-      if (pl->n_hand >= SB_HAND_MAX) { ERR(g, SB_ERR_OVERFLOW); return; }
+      if (pl->n_hand >= HAND_W) { ERR(g, SB_ERR_OVERFLOW); return; }
       CardRec r = {e->card, p[1], (e->single_use ? SB_CF_SINGLE_USE : 0) | SB_CF_OBJ, 0, 0, id};
       pl->hand[pl->n_hand++] = r;
     }
@@ -528,7 +528,7 @@ void o_effect(Game *g, int id, int pos_pt, int has_source) {
     if (o_front(g, e->x, e->y, me, &t, pts) == 0) {
       Ply *pl = &g->pl[me];
       int c = cand[o_rng_below(g, 4)];
-      if (pl->n_deck >= SB_DECK_MAX) { ERR(g, SB_ERR_OVERFLOW); return; }
+      if (pl->n_deck >= DECK_W) { ERR(g, SB_ERR_OVERFLOW); return; }
       CardRec r = {c, p[0], SB_CF_SINGLE_USE, 0, 0, -1};
       pl->deck[pl->n_deck++] = r;
     }

@@ -1,0 +1,79 @@
+"""GPU: the drop-in Python layer (reference class contracts) behaves like the oracle / the reference's callers expect."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class Cfg:
+    games_per_pairing = 2
+    max_turns = 400
+    seed = 11
+    num_workers = 128
+
+
+def test_game_contract(engine, oracle):
+    from monsoon_b200.games import Game
+    from monsoon_b200.engine import DEFAULT_DECKS, deck_indices
+    d0, d1 = (deck_indices(d) for d in DEFAULT_DECKS)
+    g = Game(seed=5, engine=engine)
+    st = oracle.new_game(5, d0, d1, 3, 2)
+    obs = g.reset()
+    assert obs.shape == (27, 5, 4) and obs.dtype == np.int32 and np.array_equal(obs, oracle.observe(st)[0])
+    for step in range(60):
+        legal = g.legal_actions()
+        m = oracle.legal_mask(st)
+        assert legal == [a for a in range(156) if m[a >> 5] >> (a & 31) & 1] and legal == sorted(legal)
+        a = legal[step % len(legal)]
+        obs, reward, done = g.step(a)
+        oracle.step(st, a)
+        assert np.array_equal(obs, oracle.observe(st)[0]) and reward in (0, 10) and done == bool(st[19] & 1)
+        assert g.to_play() == (0 if np.int8(st[16]) == 1 else 1)
+        assert g.env.have_winner() == done
+        if done:
+            break
+    assert g.action_to_string(155) == "Pass the turn" and len(g.env.actions) == 156
+
+
+def test_adapter_and_agent(engine, oracle):
+    from monsoon_b200.evo import HeuristicAgent, StormboundAdapter, WeightVector, play_game
+    from monsoon_b200.games import Game
+    np.random.seed(4)
+    w1, w2 = WeightVector(10), WeightVector(10)
+    ad = StormboundAdapter(Game(seed=9, engine=engine))
+    before = ad.game.state.clone()
+    a1 = HeuristicAgent(w1, 0)
+    legal = ad.get_legal_actions()
+    nxt = ad.apply_action(legal[0])
+    assert torch.equal(ad.game.state, before) and not torch.equal(nxt.game.state, before)  # functional apply
+    f = ad.extract_features()
+    assert f.get_feature_vector().shape == (10,) and f.get_feature_names()[0] == "mana_efficiency"
+    host = before[0].cpu().numpy()
+    a, scores, _m = oracle.select_action(host.copy(), w1.weights)
+    assert a1.select_action(ad) == a
+    assert abs(a1.score_action(ad, legal[-1]) - scores[legal[-1]]) <= 1e-5 * max(1.0, abs(scores[legal[-1]]))
+    end, turns = play_game(ad, a1, HeuristicAgent(w2, 1), max_turns=400)
+    r, acts = oracle.play_heuristic(host.copy(), w1.weights, w2.weights, 400)
+    assert turns == len(acts) and end.get_result() == r and end.is_terminal() == (r != -1 or turns < 400)
+
+
+def test_fitness_evaluator_matches_oracle(engine, oracle):
+    from monsoon_b200.evo import FitnessEvaluator, WeightVector, game_seed
+    from monsoon_b200.engine import DEFAULT_DECKS, deck_indices
+    d0, d1 = (deck_indices(d) for d in DEFAULT_DECKS)
+    np.random.seed(8)
+    pop = [WeightVector(10) for _ in range(4)]
+    ev = FitnessEvaluator(Cfg(), engine=engine)
+    fit = ev.evaluate_population(pop, generation=2)
+    want = np.zeros(4)
+    for i in range(4):
+        for j in range(4):
+            if i == j:
+                continue
+            for k in range(2):
+                st = oracle.new_game(game_seed(11, 2, i, j, k), d0, d1, 3, 2)
+                r, _ = oracle.play_heuristic(st, pop[i].weights, pop[j].weights, 400)
+                want[i] += 1.0 if r == 0 else 0.5 if r < 0 else 0.0
+    assert np.allclose(fit, want / (3 * 2)) and len(fit) == 4 and all(0 <= x <= 1 for x in fit)
+    assert len(ev.hall_of_fame) == 4 and ev.get_stats()["total_games"] == 24

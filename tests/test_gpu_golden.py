@@ -1,0 +1,72 @@
+"""GPU vs the golden fixtures produced by the reference itself (no oracle in between)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    p = os.path.join(G, name)
+    if not os.path.exists(p):
+        pytest.skip("fixture %s not generated" % name)
+    return np.load(p)
+
+
+def test_10k_default_games_rollout_kernel(engine):
+    z = load("default_chain_10k.npz")
+    ok = z["err"] == 0
+    seeds = torch.from_numpy(z["seeds"].astype(np.int64)).to(engine.device)
+    st = engine.reset(seeds)
+    chain = torch.zeros(len(seeds), dtype=torch.int64, device=engine.device)
+    steps = engine.rollout_random(st, 400, chain=chain)
+    steps, chain = steps.cpu().numpy(), chain.cpu().numpy().view(np.uint64)
+    assert np.array_equal(steps[ok], z["steps"][ok])
+    assert np.array_equal(chain[ok], z["chain"][ok])
+    host = st.cpu().numpy()
+    assert (host[~ok][:, 18] != 0).all()  # games where the reference raised are flagged
+
+
+def test_random_deck_games_rollout_kernel(engine):
+    z = load("randdeck_chain.npz")
+    dev = engine.device
+    st = engine.reset(torch.from_numpy(z["seeds"].astype(np.int64)).to(dev), torch.from_numpy(z["decks"]).to(dev),
+                      torch.from_numpy(z["factions"]).to(dev))
+    chain = torch.zeros(len(z["seeds"]), dtype=torch.int64, device=dev)
+    steps = engine.rollout_random(st, 400, chain=chain)
+    host = st.cpu().numpy()
+    steps, chain = steps.cpu().numpy(), chain.cpu().numpy().view(np.uint64)
+    unsupported = (host[:, 18] == 5) | ((host[:, 18] == 6) & (z["err"] != 2))
+    clean = (z["err"] == 0) & ~unsupported
+    assert np.array_equal(steps[clean], z["steps"][clean]) and np.array_equal(chain[clean], z["chain"][clean])
+    raised = (z["err"] != 0) & ~unsupported
+    assert (host[raised][:, 18] != 0).all() and np.array_equal(steps[raised], z["steps"][raised] + 1)
+    assert unsupported.sum() <= len(unsupported) // 100
+
+
+def test_heuristic_decisions(engine):
+    z = load("heuristic_decisions.npz")
+    st = torch.from_numpy(z["states"]).to(engine.device)
+    w = torch.from_numpy(z["weights"]).to(engine.device)
+    actions, scores = engine.select_action(st, w, want_scores=True)
+    actions, scores = actions.cpu().numpy(), scores.cpu().numpy()
+    for i in range(len(actions)):
+        ref = z["scores"][i]
+        legal = ~np.isnan(ref)
+        assert np.array_equal(legal, ~np.isnan(scores[i]))
+        np.testing.assert_allclose(scores[i][legal], ref[legal], rtol=1e-5, atol=1e-9)
+        top = np.sort(ref[legal])[::-1]
+        if len(top) == 1 or top[0] - top[1] > 1e-5 * max(1.0, abs(top[0])):
+            assert int(actions[i]) == int(z["chosen"][i]), i
+
+
+def test_heuristic_whole_games(engine):
+    z = load("heuristic_decisions.npz")
+    dev = engine.device
+    st = engine.reset(torch.from_numpy(z["game_seeds"].astype(np.int64)).to(dev))
+    res, steps = engine.rollout_heuristic(st, torch.from_numpy(z["w_first"]).to(dev), torch.from_numpy(z["w_second"]).to(dev), max_steps=400)
+    assert np.array_equal(steps.cpu().numpy(), z["game_lengths"])
+    assert np.array_equal(res.cpu().numpy(), z["game_result"])
