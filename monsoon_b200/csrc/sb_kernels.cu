@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(TPB_GAME) k_reset(int n, const unsigned long l
   if (i >= n) return;
   G g;
   init_g(g, s_cards, wt);
-  SbState s;
+  __align__(16) SbState s;  // 128-bit moves
   uint4* z = reinterpret_cast<uint4*>(&s);
   for (int k = 0; k < SB_STATE_BYTES / 16; k++) z[k] = make_uint4(0, 0, 0, 0);
   unpack(g, s);
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(TPB_GAME) k_legal_mask(int n, const u8* states
   if (i >= n) return;
   G g;
   init_g(g, s_cards, wt);
-  SbState s;
+  __align__(16) SbState s;  // 128-bit moves
   load_state(s, states + (size_t)i * SB_STATE_BYTES);
   unpack(g, s);
   u32 m[SB_MASK_WORDS];
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(TPB_GAME) k_step(int n, u8* states, const u8* 
   if (i >= n) return;
   G g;
   init_g(g, s_cards, wt);
-  SbState s;
+  __align__(16) SbState s;  // 128-bit moves
   load_state(s, states + (size_t)i * SB_STATE_BYTES);
   unpack(g, s);
   game_step(g, actions[i]);
@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(TPB_GAME) k_observe(int n, const u8* states, i
   if (i >= n) return;
   G g;
   init_g(g, s_cards, wt);
-  SbState s;
+  __align__(16) SbState s;  // 128-bit moves
   load_state(s, states + (size_t)i * SB_STATE_BYTES);
   unpack(g, s);
   int e = observe(g, obs + (size_t)i * SB_OBS_INTS);
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(TPB_GAME) k_features(int n, const u8* states, 
   if (i >= n) return;
   G g;
   init_g(g, s_cards, wt);
-  SbState s;
+  __align__(16) SbState s;  // 128-bit moves
   load_state(s, states + (size_t)i * SB_STATE_BYTES);
   unpack(g, s);
   double f[SB_N_FEATURES];
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(TPB_GAME) k_features(int n, const u8* states, 
 // whole uniform-random rollout in one launch; HBM is touched once on the way in and once on the way out
 template <bool DIGEST>
 SBD_FI void rollout_random_body(G& g, u8* state_ptr, int max_steps, int* steps_slot, unsigned long long* chain_slot) {
-  SbState s;
+  __align__(16) SbState s;  // 128-bit moves
   load_state(s, state_ptr);
   unpack(g, s);
   unsigned long long ch = DIGEST ? *chain_slot : 0ull;
@@ -221,7 +221,8 @@ SBD_FI Best warp_argmax(Best b) {  // np.argmax: first maximum = lowest action i
 SBD_FI double score_delta(const double* w, const double* fc, const double* fn) {  // evo/heuristic_agent.py:23-51,82-122
   double d = 0.0;
 #pragma unroll
-  for (int i = 0; i < SB_N_FEATURES; i++) d = __dadd_rn(d, __dmul_rn(w[i], __dsub_rn(fn[i], fc[i])));
+  // np.dot at n = 10 is OpenBLAS's scalar tail loop with FMA contraction: sequential fused multiply-add
+  for (int i = 0; i < SB_N_FEATURES; i++) d = __fma_rn(w[i], __dsub_rn(fn[i], fc[i]), d);
   double eff = __dsub_rn(fn[0], fc[0]);
   double rp = eff < -0.3 ? __dmul_rn(fabs(eff), 0.2) : 0.0;
   return __dsub_rn(__dsub_rn(-d, d), rp);

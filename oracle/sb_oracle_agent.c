@@ -5,6 +5,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <pthread.h>
+#include <math.h>
 #include "sb_oracle.h"
 
 void sbo_step(SbState *s, int action);
@@ -188,7 +189,9 @@ int sbo_select_action(const SbState *s, const double *w, double *scores, uint32_
     if (!nerr) nerr = sbo_features(&nx, fn);
     if (!nerr && !cur_err) {
       double d = 0.0;
-      for (int i = 0; i < SB_N_FEATURES; i++) d += w[i] * (fn[i] - fc[i]);
+      /* np.dot for n = 10 (OpenBLAS ddot, n < 32: scalar tail loop compiled with FMA contraction) ==
+       * sequential fused multiply-add; verified bit-exact against numpy 2.3.5 / OpenBLAS 0.3.30 */
+      for (int i = 0; i < SB_N_FEATURES; i++) d = fma(w[i], fn[i] - fc[i], d);
       double eff = fn[0] - fc[0];
       double rp = eff < -0.3 ? (eff < 0 ? -eff : eff) * 0.2 : 0.0;
       sc = (-d) - d - rp;

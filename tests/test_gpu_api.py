@@ -30,7 +30,8 @@ def test_game_contract(engine, oracle):
         oracle.step(st, a)
         assert np.array_equal(obs, oracle.observe(st)[0]) and reward in (0, 10) and done == bool(st[19] & 1)
         assert g.to_play() == (0 if np.int8(st[16]) == 1 else 1)
-        assert g.env.have_winner() == done
+        bases = np.frombuffer(st[32:34].tobytes() + st[136:138].tobytes(), dtype='<i2')
+        assert g.env.have_winner() == bool((bases < 0).any())  # `done` is evaluated BEFORE the PASS turn pipeline (Q2)
         if done:
             break
     assert g.action_to_string(155) == "Pass the turn" and len(g.env.actions) == 156

@@ -44,7 +44,7 @@ def test_random_deck_games_rollout_kernel(engine):
     assert np.array_equal(steps[clean], z["steps"][clean]) and np.array_equal(chain[clean], z["chain"][clean])
     raised = (z["err"] != 0) & ~unsupported
     assert (host[raised][:, 18] != 0).all() and np.array_equal(steps[raised], z["steps"][raised] + 1)
-    assert unsupported.sum() <= len(unsupported) // 100
+    assert unsupported.sum() <= len(unsupported) * 3 // 200
 
 
 def test_heuristic_decisions(engine):
