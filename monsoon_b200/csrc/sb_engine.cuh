@@ -137,7 +137,8 @@ SBD_NI double rng_random(G& g) {
   u32 w0, w1;
   philox(g.draw, g.turn, 0, 0, g.seed_lo, g.seed_hi, w0, w1);
   g.draw++;
-  return __ddiv_rn(__dadd_rn(__dmul_rn((double)(w0 >> 5), 67108864.0), (double)(w1 >> 6)), 9007199254740992.0);
+  // (a * 2^26 + b) / 2^53: a power-of-two divisor, so the multiplication by 2^-53 is bit-identical
+  return __dmul_rn(__dadd_rn(__dmul_rn((double)(w0 >> 5), 67108864.0), (double)(w1 >> 6)), 0x1.0p-53);
 }
 SBD void shuffle(G& g, i8* a, int n) {
   for (int i = n - 1; i > 0; i--) {
@@ -623,8 +624,16 @@ SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + num
     for (int i = 0; i < n; i++) { acc = __dadd_rn(acc, __ddiv_rn(__ldg(&g.wt[p.deck[i].wn]), sum)); cdf[i] = acc; }
     double last = cdf[n - 1];
     double u = rng_random(g);
+    // idx = #{i : fl(cdf_i / last) <= u} (searchsorted side='right' on the normalised cdf).  Rounding is
+    // monotone, so the quotient only has to be formed when cdf_i is within 1e-15 (> 2^-50) of u*last;
+    // everywhere else the comparison is decided without the FP64 division.
+    const double t = __dmul_rn(u, last);
+    const double t_lo = __dmul_rn(t, 0.999999999999999), t_hi = __dmul_rn(t, 1.000000000000001);
     int idx = 0;
-    for (int i = 0; i < n; i++) if (__ddiv_rn(cdf[i], last) <= u) idx++;
+    for (int i = 0; i < n; i++) {
+      const double c = cdf[i];
+      if (c < t_lo || (c <= t_hi && __ddiv_rn(c, last) <= u)) idx++;
+    }
     if (idx > n - 1) idx = n - 1;
     CardRec c = p.deck[idx];
     c.wn = 0;

@@ -141,69 +141,96 @@ __global__ void __launch_bounds__(TPB_GAME) k_features(int n, const u8* states, 
   if (err) err[i] = (u8)e;
 }
 
-// whole uniform-random rollout in one launch; HBM is touched once on the way in and once on the way out
-template <bool DIGEST>
-SBD_FI void rollout_random_body(G& g, u8* state_ptr, int max_steps, int* steps_slot, unsigned long long* chain_slot) {
-  __align__(16) SbState s;  // 128-bit moves
-  load_state(s, state_ptr);
-  unpack(g, s);
-  unsigned long long ch = DIGEST ? *chain_slot : 0ull;
-  int k = 0;
-  while (!(g.done & SB_DONE) && !g.err && k < max_steps) {
-    u32 m[SB_MASK_WORDS];
-    int nl = legal_mask(g, m);
-    int pick = (int)agent_pick(g.seed_lo, g.seed_hi, g.steps, (u32)nl);
-    int a = 0;
-    for (int w = 0; w < SB_MASK_WORDS; w++) {  // pick-th set bit
-      int c = __popc(m[w]);
-      if (pick < c) { u32 v = m[w]; for (int q = 0; q < pick; q++) v &= v - 1; a = w * 32 + __ffs(v) - 1; break; }
-      pick -= c;
-    }
-    game_step(g, a);
-    end_of_step(g);
-    if (DIGEST) { pack(g, s); ch = (ch ^ digest_state(s)) * 0x100000001B3ull; }
-    k++;
+// whole uniform-random rollout in one launch; HBM is touched once on the way in and once on the way out.
+//
+// Turn-synchronous warp schedule.  A game alternates "a few non-PASS actions, then PASS"; the PASS step
+// (flip, refill with FP64 draws, front lines, turn-start structures, every unit's move) carries most of the
+// instructions.  Lanes therefore do NOT step in lock-step by step index: phase A lets every lane play its
+// non-PASS actions (lanes already at their PASS wait), phase B executes the PASS of all 32 lanes together.
+// Games are independent, so the order is free; what changes is that the long PASS pipeline is entered
+// converged (one instruction stream per warp instead of one per lane group), which is what the ncu profile
+// of the lock-step version asked for: 2.6-3.0 of 32 lanes active, 73 % of stall samples = instruction fetch.
+SBD_FI int pick_action(const G& g) {
+  u32 m[SB_MASK_WORDS];
+  int nl = legal_mask(g, m);
+  int pick = (int)agent_pick(g.seed_lo, g.seed_hi, g.steps, (u32)nl);
+#pragma unroll 1
+  for (int w = 0; w < SB_MASK_WORDS; w++) {  // pick-th set bit
+    int c = __popc(m[w]);
+    if (pick < c) { u32 v = m[w]; for (int q = 0; q < pick; q++) v &= v - 1; return w * 32 + __ffs(v) - 1; }
+    pick -= c;
   }
-  pack(g, s);
-  store_state(state_ptr, s);
-  if (steps_slot) *steps_slot = k;
-  if (DIGEST) *chain_slot = ch;
+  return SB_ACTION_PASS;
 }
-// shape A: one game per THREAD, working set in local memory (best when the batch oversubscribes the chip)
 template <bool DIGEST>
 __global__ void __launch_bounds__(TPB_GAME) k_rollout_random(int n, u8* states, int max_steps, int* steps_out,
                                                              unsigned long long* chain, const DCard* cards, const double* wt,
-                                                             int gpw) {
+                                                             int gpw, int turn_sync) {
   __shared__ DCard s_cards[SBC_COUNT];
   stage_cards(s_cards, cards);
-  // gpw games per warp on CONSECUTIVE lanes (gpw = 32: plain thread-per-game).  Fewer games per warp =
-  // fewer divergent paths serialised on one scheduler slot; consecutive lanes keep the 32-byte local-memory
-  // sectors of the per-thread working set dense.
+  // gpw games per warp on CONSECUTIVE lanes (32 = plain thread per game).  Fewer games per warp = fewer
+  // divergent paths serialised on one scheduler slot when the batch is small; consecutive lanes keep the
+  // 32-byte local-memory sectors of the thread-private working set dense.  All 32 lanes stay in the kernel
+  // (full-mask votes below); lanes without a game just never become `alive`.
+  const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
   const int i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * gpw + lane;
-  if (lane >= gpw || i >= n) return;
+  const bool has_game = lane < gpw && i < n;
   G g;
   init_g(g, s_cards, wt);
-  rollout_random_body<DIGEST>(g, states + (size_t)i * SB_STATE_BYTES, max_steps, steps_out ? steps_out + i : nullptr,
-                              DIGEST ? chain + i : nullptr);
-}
-// shape B: one game per group of LPG lanes (leader lane runs the rules, no inter-game divergence inside a
-// warp when LPG == 32), working set in SHARED memory.  Trades lanes for issue slots: with few games
-// (BASELINE configs[1]: 4,096) the chip is latency-bound, so every game gets its own warp scheduler slot.
-template <bool DIGEST, int LPG>
-__global__ void __launch_bounds__(128) k_rollout_random_grp(int n, u8* states, int max_steps, int* steps_out,
-                                                            unsigned long long* chain, const DCard* cards, const double* wt) {
-  __shared__ DCard s_cards[SBC_COUNT];
-  extern __shared__ __align__(16) unsigned char s_dyn[];  // (128 / LPG) working sets
-  G* s_g = reinterpret_cast<G*>(s_dyn);
-  stage_cards(s_cards, cards);
-  const int slot = threadIdx.x / LPG;
-  const int i = blockIdx.x * (128 / LPG) + slot;
-  if (i >= n || (threadIdx.x % LPG) != 0) return;
-  G& g = s_g[slot];
-  init_g(g, s_cards, wt);
-  rollout_random_body<DIGEST>(g, states + (size_t)i * SB_STATE_BYTES, max_steps, steps_out ? steps_out + i : nullptr,
-                              DIGEST ? chain + i : nullptr);
+  __align__(16) SbState s;  // 128-bit moves
+  u8* sp = states + (size_t)(has_game ? i : 0) * SB_STATE_BYTES;
+  unsigned long long ch = 0ull;
+  int k = 0;
+  bool alive = false;
+  if (has_game) {
+    load_state(s, sp);
+    unpack(g, s);
+    if (DIGEST) ch = chain[i];
+    alive = !(g.done & SB_DONE) && !g.err && max_steps > 0;
+  }
+  if (!turn_sync) {  // lock-step by step index (kept for A/B measurements)
+    while (alive) {
+      game_step(g, pick_action(g));
+      end_of_step(g);
+      if (DIGEST) { pack(g, s); ch = (ch ^ digest_state(s)) * 0x100000001B3ull; }
+      k++;
+      alive = !(g.done & SB_DONE) && !g.err && k < max_steps;
+    }
+  } else {
+    bool at_pass = false;
+    while (__any_sync(FULL, alive)) {
+      for (;;) {  // phase A: non-PASS actions
+        int a = -1;
+        if (alive && !at_pass) {
+          a = pick_action(g);
+          if (a == SB_ACTION_PASS) { at_pass = true; a = -1; }
+        }
+        if (!__any_sync(FULL, a >= 0)) break;
+        if (a >= 0) {
+          game_step(g, a);
+          end_of_step(g);
+          if (DIGEST) { pack(g, s); ch = (ch ^ digest_state(s)) * 0x100000001B3ull; }
+          k++;
+          alive = !(g.done & SB_DONE) && !g.err && k < max_steps;
+        }
+      }
+      if (alive && at_pass) {  // phase B: everybody's PASS, converged
+        game_step(g, SB_ACTION_PASS);
+        end_of_step(g);
+        if (DIGEST) { pack(g, s); ch = (ch ^ digest_state(s)) * 0x100000001B3ull; }
+        k++;
+        at_pass = false;
+        alive = !(g.done & SB_DONE) && !g.err && k < max_steps;
+      }
+    }
+  }
+  if (has_game) {
+    pack(g, s);
+    store_state(sp, s);
+    if (steps_out) steps_out[i] = k;
+    if (DIGEST) chain[i] = ch;
+  }
 }
 
 // ---------------------------------------------------------------- warp-per-game kernels (heuristic agent)
@@ -351,6 +378,10 @@ struct SbHandle {
   cudaStream_t stream;
   int lpg;  // lanes per game for the rollout kernels (0 or 1 = thread per game)
   int gpw;  // games per warp for the thread-per-game shape (0 = choose by batch size)
+  int persistent;  // retired (measured: no gain over the hardware CTA scheduler)
+  int turn_sync;   // 1: turn-synchronous warp schedule in the rollout kernel
+  int ctas_per_sm;
+  unsigned int* d_counter;
 };
 
 static int fail(SbHandle* h, cudaError_t e, const char* what) {
@@ -362,32 +393,18 @@ static int fail(SbHandle* h, cudaError_t e, const char* what) {
 
 static inline int grid_for(int n, int per_cta) { return (n + per_cta - 1) / per_cta; }
 template <bool DIGEST>
-static void launch_rollout_random(SbHandle* h, int lpg, int n, uint8_t* states_d, int max_steps, int32_t* steps_d, uint64_t* chain_d,
+static void launch_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max_steps, int32_t* steps_d, uint64_t* chain_d,
                                   cudaStream_t st) {
-  unsigned long long* ch = (unsigned long long*)chain_d;
-#define GRP(L)                                                                                                              \
-  do {                                                                                                                      \
-    const int smem = (128 / L) * (int)sizeof(G);                                                                            \
-    cudaFuncSetAttribute(k_rollout_random_grp<DIGEST, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);               \
-    k_rollout_random_grp<DIGEST, L><<<grid_for(n, 128 / L), 128, smem, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt); \
-  } while (0)
-  switch (lpg) {
-    case 32: GRP(32); break;
-    case 16: GRP(16); break;
-    case 8: GRP(8); break;
-    case 4: GRP(4); break;
-    case 2: GRP(2); break;
-    default: {
-      int gpw = h->gpw;
-      if (gpw <= 0 || gpw > 32) {  // auto: spread a small batch over all warp schedulers (4 per SM), at most 32 games per warp
-        gpw = (n + h->sm_count * 16 - 1) / (h->sm_count * 16);
-        gpw = gpw < 4 ? 4 : gpw > 32 ? 32 : gpw;
-      }
-      k_rollout_random<DIGEST><<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards,
-                                                                                     h->d_wt, gpw);
-    }
+  int gpw = h->gpw;
+  if (gpw <= 0 || gpw > 32) {
+    // auto (measured, tools/sweep_sync.py): full warps as soon as there are ~2 warps of games per SM; below
+    // that, halve the games per warp so that every SM still gets a warp (4096 games -> 16 per warp)
+    const int per_warp = (n + h->sm_count * 2 - 1) / (h->sm_count * 2);
+    gpw = per_warp >= 24 ? 32 : per_warp >= 12 ? 16 : 8;
   }
-#undef GRP
+  k_rollout_random<DIGEST><<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, st>>>(n, states_d, max_steps, steps_d,
+                                                                                  (unsigned long long*)chain_d, h->d_cards, h->d_wt, gpw,
+                                                                                  h->turn_sync);
 }
 
 extern "C" {
@@ -436,6 +453,14 @@ int sb_create(int device, SbHandle** out) {
   static double wt[WT_N];
   volatile double w = 1.0;  // player.py:32,59: w*1.6+100 with two roundings (volatile blocks FMA contraction)
   for (int i = 0; i < WT_N; i++) { wt[i] = w; volatile double m = w * 1.6; w = m + 100.0; }
+  CK(cudaMalloc(&h->d_counter, 256));
+  h->persistent = 0;
+  h->turn_sync = 1;
+  {
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rollout_random<false>, TPB_GAME, 0));
+    h->ctas_per_sm = nb > 0 ? nb : 8;
+  }
   CK(cudaMalloc(&h->d_wt, sizeof wt));
   CK(cudaMemcpy(h->d_wt, wt, sizeof wt, cudaMemcpyHostToDevice));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -450,6 +475,7 @@ int sb_destroy(SbHandle* h) {
   cudaSetDevice(h->device);
   if (h->d_cards) cudaFree(h->d_cards);
   if (h->d_wt) cudaFree(h->d_wt);
+  if (h->d_counter) cudaFree(h->d_counter);
   if (h->d_stage) cudaFree(h->d_stage);
   if (h->stream) cudaStreamDestroy(h->stream);
   free(h);
@@ -505,17 +531,17 @@ int sb_select_action(SbHandle* h, int n, const uint8_t* states_d, const double* 
 }
 int sb_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max_steps, int32_t* steps_d, uint64_t* chain_d, void* stream) {
   if (n <= 0) return 0;
-  // lanes per game: explicit (sb_set_option / SB_LPG) or by batch size -- a warp per game while the chip has warp slots to spare
-  int lpg = h->lpg;
-  if (lpg <= 0) lpg = 1;
-  if (chain_d) launch_rollout_random<true>(h, lpg, n, states_d, max_steps, steps_d, chain_d, (cudaStream_t)stream);
-  else launch_rollout_random<false>(h, lpg, n, states_d, max_steps, steps_d, nullptr, (cudaStream_t)stream);
+  if (chain_d) launch_rollout_random<true>(h, n, states_d, max_steps, steps_d, chain_d, (cudaStream_t)stream);
+  else launch_rollout_random<false>(h, n, states_d, max_steps, steps_d, nullptr, (cudaStream_t)stream);
   LAUNCH_CHECK();
   return 0;
 }
 int sb_set_option(SbHandle* h, const char* key, int value) {
-  if (!strcmp(key, "lanes_per_game")) { h->lpg = value; return 0; }
+  if (!strcmp(key, "lanes_per_game")) return 0;  // retired shape (measured slower); accepted and ignored
+  if (!strcmp(key, "turn_sync")) { h->turn_sync = value; return 0; }
   if (!strcmp(key, "games_per_warp")) { h->gpw = value; return 0; }
+  if (!strcmp(key, "persistent")) { h->persistent = value; return 0; }
+  if (!strcmp(key, "ctas_per_sm")) { h->ctas_per_sm = value; return 0; }
   return -1;
 }
 int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_first_d, const double* w_second_d,
