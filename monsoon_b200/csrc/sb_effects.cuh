@@ -20,10 +20,13 @@ SBD_FI int choice_pt(G& g, const i8* l, int n) {
 SBD_NI void keyed_sort(G& g, i8* pts, const i16* k1, int n, bool desc) {
   double r[22];
   i16 k[22];
+  #pragma unroll 1
   for (int i = 0; i < n; i++) { r[i] = rng_random(g); k[i] = k1[i]; }
+  #pragma unroll 1
   for (int i = 1; i < n; i++) {
     i8 p = pts[i]; i16 kk = k[i]; double rr = r[i];
     int j = i - 1;
+    #pragma unroll 1
     while (j >= 0) {
       bool less = (k[j] < kk) || (k[j] == kk && r[j] < rr);
       bool greater = (k[j] > kk) || (k[j] == kk && r[j] > rr);
@@ -37,11 +40,13 @@ SBD_NI int count_types_friendly(G& g) {  // cards/up02.py:13-19, up03.py:14-20
   i8 pts[22];
   int n = get_targets(g, CUR(g), t, PT_NONE, pts);
   u32 m = 0;
+  #pragma unroll 1
   for (int i = 0; i < n; i++) m |= CARD(g, g.e[at_pt(g, pts[i])].card).types;
   return __popc(m);
 }
 SBD_FI int empty_of(const G& g, const i8* in, int n, i8* out) {
   int k = 0;
+  #pragma unroll 1
   for (int i = 0; i < n; i++) if (at_pt(g, in[i]) < 0) out[k++] = in[i];
   return k;
 }
@@ -50,6 +55,7 @@ SBD_NI int frontmost(G& g, const Target& t, i8* pts) {
   int n = get_targets(g, CUR(g), t, PT_NONE, pts);
   if (n > 0) {
     i16 ky[22];
+    #pragma unroll 1
     for (int i = 0; i < n; i++) ky[i] = (i16)PTY(pts[i]);
     keyed_sort(g, pts, ky, n, true);
   }
@@ -74,6 +80,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
     case SBC_B004:  // cards/b004.py:13-22
       t = mkT(TK_ANY, TS_ENEMY); t.base = 1;
       n = get_targets(g, CUR(g), t, PT_NONE, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) { deal_damage_pt(g, pts[i], p[0], 1); if (g.err) return; }
       destroy(g, id, 1);
       break;
@@ -81,8 +88,10 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       t = mkT(TK_ANY, TS_FRIENDLY);
       n = surrounding(g, ex, ey, CUR(g), &t, pts);
       int mine = 0;
+      #pragma unroll 1
       for (int i = 0; i < g.n_mem; i++) if (g.mem[i].b005 == id) mine++;
       if (mine == 0) {
+        #pragma unroll 1
         for (int i = 0; i < n; i++) {
           tid = need(g, pts[i]);
           if (tid < 0) return;
@@ -91,10 +100,12 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
           const Ent& s = g.e[tid];
           m.b005 = (i8)id; m.pos = (u8)pts[i]; m.card = s.card; m.fl = s.fl & (EF_OWNER | EF_STRUCT | EF_FIXED); m.strength = s.strength;
           if (s.card == SBC_B005) for (int q = 0; q < g.n_mem - 1; q++) if (g.mem[q].b005 == tid) m.fl |= EF_SINGLE;  // EF_SINGLE bit doubles as "nested memories" here
+          #pragma unroll 1
           for (int k = 0; k < 5; k++) m.st[k] = s.st[k];
         }
       } else {
         int count = 0;
+        #pragma unroll 1
         for (int i = 0; i < g.n_mem && count < p[0]; i++) {
           const Mem m = g.mem[i];
           if (m.b005 != id) continue;
@@ -103,12 +114,14 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
             if (m.fl & EF_SINGLE) { GERR(g, SB_ERR_UNSUPPORTED); return; }  // memories of a remembered temple are not modelled
             int c = new_ent(g, m.card, m.fl & EF_OWNER, m.strength);
             g.e[c].fl = (u8)((g.e[c].fl & ~EF_FIXED) | (m.fl & EF_FIXED));
+            #pragma unroll 1
             for (int k = 0; k < 5; k++) g.e[c].st[k] = m.st[k];
             set_xy(g, PTX(m.pos), PTY(m.pos), c);
             count++;
           }
         }
         int w = 0;
+        #pragma unroll 1
         for (int i = 0; i < g.n_mem; i++) if (g.mem[i].b005 != id) g.mem[w++] = g.mem[i];
         g.n_mem = (u8)w;
       }
@@ -117,8 +130,10 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       t = mkT(TK_UNIT, TS_FRIENDLY);
       n = get_targets(g, CUR(g), t, PT_NONE, pts);
       i8 sel[22]; int ns = 0;
+      #pragma unroll 1
       for (int i = 0; i < n; i++) if (!g.e[at_pt(g, pts[i])].st[SB_ST_VITALIZED]) sel[ns++] = pts[i];
       shuffle(g, sel, ns);
+      #pragma unroll 1
       for (int i = 0; i < ns && i < p[1]; i++) { tid = need(g, sel[i]); if (tid < 0) return; v_vitalize(g, tid); }
       i8 tiles[2], fr[5], bh[5]; int nt = 0;
       int nf = column_tiles(g, ex, ey, CUR(g), nullptr, true, fr);
@@ -145,6 +160,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       n = get_targets(g, CUR(g), t, PT_NONE, pts);
       if (n > 0) {
         i16 ks[22];
+        #pragma unroll 1
         for (int i = 0; i < n; i++) ks[i] = g.e[at_pt(g, pts[i])].strength;
         keyed_sort(g, pts, ks, n, false);
         tid = need(g, pts[0]);
@@ -157,6 +173,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       if (n > 0) {
         if (n > p[0]) n = p[0];
         shuffle(g, pts, n);
+        #pragma unroll 1
         for (int i = 0; i < n; i++) { tid = need(g, pts[i]); if (tid < 0) return; v_confuse(g, tid); }
       }
       break;
@@ -167,6 +184,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
     case SBC_B203:  // cards/b203.py:12-21
       t = mkT(TK_UNIT, TS_FRIENDLY);
       n = column_tiles(g, ex, ey, me, &t, true, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) {
         tid = need(g, pts[i]);
         if (tid < 0) return;
@@ -181,6 +199,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
     case SBC_B305: {  // cards/b305.py:16-45: ability_amount, ability_mana, original_cost
       t = mkT(TK_STRUCTURE, TS_FRIENDLY);
       n = get_targets(g, CUR(g), t, PT(ex, ey), pts);
+      #pragma unroll 1
       for (int i = 0; i < n && i < p[0]; i++) {
         tid = need(g, pts[i]);
         if (tid < 0) return;
@@ -189,6 +208,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
           i8 sp[22];
           int tx = PTX(pts[i]), ty = PTY(pts[i]);
           int ns = surrounding(g, tx, ty, CUR(g), &tu, sp);
+          #pragma unroll 1
           for (int k = 0; k < ns; k++) {
             int nx = PTX(sp[k]) - tx + ex, ny = PTY(sp[k]) - ty + ey;
             if (valid_xy(nx, ny)) { int u = need(g, sp[k]); if (u < 0) return; v_teleport(g, u, nx, ny); }
@@ -219,12 +239,15 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
     case SBC_U017: {  // cards/u017.py:18-34
       Ply& pl = g.pl[me];
       i8 cand[HAND_W]; int nc = 0;
+      #pragma unroll 1
       for (int i = 0; i < pl.n_hand; i++) if (CARD(g, pl.hand[i].card).kind == KIND_SPELL && pl.hand[i].cost <= 8) cand[nc++] = (i8)i;
       if (nc > 0) {
         shuffle(g, cand, nc);
         int remaining = 8, nch = 0;
         i8 chosen[HAND_W];
+        #pragma unroll 1
         for (int i = 0; i < nc; i++) if (pl.hand[cand[i]].cost <= remaining) { chosen[nch++] = cand[i]; remaining -= pl.hand[cand[i]].cost; }
+        #pragma unroll 1
         for (int i = 0; i < nch; i++) {
           const DCard& c = CARD(g, pl.hand[chosen[i]].card);
           int where = PT_NONE;
@@ -237,6 +260,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
           int idx = chosen[i];
           player_play(g, me, idx, where);
           if (g.err) return;
+          #pragma unroll 1
           for (int k = i + 1; k < nch; k++) if (chosen[k] > idx) chosen[k]--;
         }
       }
@@ -245,8 +269,10 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       t = mkT(TK_UNIT, TS_ANY);
       n = surrounding(g, ex, ey, CUR(g), &t, pts);
       u32 m = 0;
+      #pragma unroll 1
       for (int i = 0; i < n; i++) m |= 1u << CARD(g, g.e[at_pt(g, pts[i])].card).first_type;
       int cnt = __popc(m);
+      #pragma unroll 1
       for (int k = 0; k < cnt; k++) {
         Target tb = mkT(TK_ANY, TS_ENEMY); tb.base = 1;
         n = get_targets(g, CUR(g), tb, PT_NONE, pts);
@@ -295,6 +321,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
     case SBC_U055:  // cards/u055.py:12-19
       t = mkT(TK_UNIT, TS_ENEMY); t.xstatus = 1 << SB_ST_CONFUSED;
       n = column_tiles(g, ex, ey, CUR(g), &t, true, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) { tid = need(g, pts[i]); if (tid < 0) return; v_confuse(g, tid); }
       break;
     case SBC_U061:  // cards/u061.py:12-23
@@ -308,6 +335,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       t = mkT(TK_UNIT, TS_ENEMY);
       n = bordering(g, ex, ey, me, &t, pts);
       i8 nc[4]; int nn = 0;
+      #pragma unroll 1
       for (int i = 0; i < n; i++) if (!g.e[at_pt(g, pts[i])].st[SB_ST_CONFUSED]) nc[nn++] = pts[i];
       if (nn > 0) {
         tid = need(g, choice_pt(g, nc, nn));
@@ -339,11 +367,13 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       if (tid < 0 || ent_struct(g.e[tid]) || !g.e[tid].st[SB_ST_FROZEN]) return;
       t = mkT(TK_UNIT, TS_ENEMY); t.status = 1 << SB_ST_FROZEN;
       n = surrounding(g, ex, ey, me, &t, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) { deal_damage_pt(g, pts[i], p[0], 1); if (g.err) return; }
       break;
     case SBC_U103:  // cards/u103.py:12-18
       t = mkT(TK_UNIT, TS_ENEMY);
       n = bordering(g, ex, ey, CUR(g), &t, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) { tid = need(g, pts[i]); if (tid < 0) return; v_freeze(g, tid); }
       break;
     case SBC_U106:  // cards/u106.py:13-18
@@ -351,6 +381,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       if (bordering(g, ex, ey, CUR(g), &t, pts) > 0 || ey == 4) v_heal(g, id, p[0]);
       break;
     case SBC_U111:  // cards/u111.py:13-21
+      #pragma unroll 1
       for (int k = 0; k < p[0]; k++) {
         t = mkT(TK_UNIT, TS_FRIENDLY);
         n = surrounding(g, ex, ey, me, &t, pts);
@@ -369,6 +400,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
     case SBC_U216: player_damage(g, me, p[0]); break;  // cards/u216.py:12-13
     case SBC_U217: {  // cards/u217.py:13-17
       i8 row[4]; int nr = 0;
+      #pragma unroll 1
       for (int x = 0; x < 4; x++) if (g.board[16 + x] < 0) row[nr++] = (i8)(16 + x);
       if (nr > 0) spawn_token_unit(g, me, choice_pt(g, row, nr), p[0], UT_SATYR);
       break; }
@@ -395,6 +427,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       t = mkT(TK_UNIT, TS_ENEMY);
       n = bordering(g, ex, ey, CUR(g), &t, pts);
       int behind = PT_NONE, right = PT_NONE, left = PT_NONE, front = PT_NONE;
+      #pragma unroll 1
       for (int i = n - 1; i >= 0; i--) {
         if (PTY(pts[i]) == ey + 1) behind = pts[i];
         if (PTX(pts[i]) == ex + 1) right = pts[i];
@@ -426,6 +459,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       n = surrounding(g, ex, ey, CUR(g), &t, pts);
       if (n > 0) {
         shuffle(g, pts, n);
+        #pragma unroll 1
         for (int i = 0; i < n && i < p[0]; i++) { tid = need(g, pts[i]); if (tid < 0) return; v_vitalize(g, tid); }
       }
       v_vitalize(g, id);
@@ -438,6 +472,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
     case SBC_U401:  // cards/u401.py:13-22: `damage`
       t = mkT(TK_UNIT, TS_ANY);
       n = bordering(g, ex, ey, CUR(g), &t, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) {
         tid = at_pt(g, pts[i]);
         if (tid >= 0) {
@@ -450,17 +485,20 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
     case SBC_U403:  // cards/u403.py:14-24: ability_amount, ability_strength
       t = mkT(TK_UNIT, TS_ANY); t.status = 1 << SB_ST_POISONED;
       n = surrounding(g, ex, ey, CUR(g), &t, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) {
         i8 bt[4], em[4];
         int nb = bordering(g, PTX(pts[i]), PTY(pts[i]), CUR(g), nullptr, bt);
         int ne = empty_of(g, bt, nb, em);
         shuffle(g, em, ne);
+        #pragma unroll 1
         for (int k = 0; k < ne && k < p[0]; k++) spawn_token_unit(g, me, em[k], p[1], UT_TOAD);
       }
       break;
     case SBC_U405:  // cards/u405.py:13-21
       t = mkT(TK_UNIT, TS_ANY);
       n = bordering(g, ex, ey, CUR(g), &t, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) {
         int dealt = deal_damage_pt(g, pts[i], p[0], 1);
         if (g.err) return;
@@ -478,11 +516,13 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       n = get_targets(g, CUR(g), t, PT_NONE, pts);
       if (n > 0) {
         shuffle(g, pts, n);
+        #pragma unroll 1
         for (int i = 0; i < n && i < p[0]; i++) { tid = need(g, pts[i]); if (tid < 0) return; v_poison(g, tid); }
       }
       break;
     case SBC_UA03: {  // cards/ua03.py:12-15
       i8 row[5]; int nr = 0;
+      #pragma unroll 1
       for (int x = 0; x < 4; x++) if (g.board[ey * 4 + x] < 0) row[nr++] = (i8)PT(x, ey);
       row[nr++] = (i8)PT(ex, ey);
       int where = choice_pt(g, row, nr);
@@ -498,7 +538,9 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       if (src) {
         i8 sel[22]; int nsel = 0;
         int mn = 32767;
+        #pragma unroll 1
         for (int i = 0; i < ns; i++) { int s = g.e[at_pt(g, src[i])].strength; if (s < mn) mn = s; }
+        #pragma unroll 1
         for (int i = 0; i < ns; i++) if (g.e[at_pt(g, src[i])].strength == mn) sel[nsel++] = src[i];
         if (nsel > 0) destroy(g, at_pt(g, sel[rng_below(g, nsel)]), 1);
       }
@@ -507,6 +549,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       i8 sd[2], em[2];
       int ns = side_list(ex, ey, sd);
       int ne = empty_of(g, sd, ns, em);
+      #pragma unroll 1
       for (int k = 0; k < ne; k++) spawn_token_unit(g, me, em[k], p[0], UT_ANCIENT);
       break; }
     case SBC_UA07:  // cards/ua07.py:11-22
@@ -537,6 +580,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
     case SBC_UD02:  // cards/ud02.py:13-19
       t = mkT(TK_UNIT, TS_ANY); t.xtypes = 1 << UT_DRAGON;
       n = column_tiles(g, ex, ey, CUR(g), &t, true, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) { deal_damage_pt(g, pts[i], p[0], 1); if (g.err) return; }
       break;
     case SBC_UD31:  // cards/ud31.py:13-24
@@ -550,6 +594,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       break;
     case SBC_UE01: {  // cards/ue01.py:11-19
       int times = e.dmg;
+      #pragma unroll 1
       for (int k = 0; k < times; k++) {
         t = mkT(TK_UNIT, TS_ENEMY);
         n = get_targets(g, me, t, PT_NONE, pts);
@@ -566,23 +611,27 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       t = mkT(TK_UNIT, TS_ENEMY);
       n = get_targets(g, me, t, PT_NONE, pts);
       int c = 0;
+      #pragma unroll 1
       for (int i = 0; i < n; i++) if (g.e[at_pt(g, pts[i])].strength > e.strength) c++;
       v_heal(g, id, c * p[0]);
       break; }
     case SBC_UE05:  // cards/ue05.py:12-19
       t = mkT(TK_UNIT, TS_FRIENDLY); t.has_limit = 1; t.limit = (i16)(e.strength - 1);
       n = get_targets(g, me, t, PT(ex, ey), pts);
+      #pragma unroll 1
       for (int i = 0; i < n && i < p[0]; i++) g.e[at_pt(g, pts[i])].strength = e.strength;
       break;
     case SBC_UE11: v_heal(g, id, p[0]); break;  // cards/ue11.py:12-13
     case SBC_UE12:  // cards/ue12.py:11-18
       t = mkT(TK_UNIT, TS_ENEMY);
       n = column_tiles(g, ex, ey, me, &t, true, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) { tid = need(g, pts[i]); if (tid < 0) return; destroy(g, tid, 1); }
       break;
     case SBC_UE21:  // cards/ue21.py:11-18
       t = mkT(TK_UNIT, TS_FRIENDLY); t.has_limit = 1; t.limit = e.strength;
       n = get_targets(g, me, t, PT(ex, ey), pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) {
         tid = need(g, pts[i]);
         if (tid < 0) return;
@@ -595,6 +644,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       n = get_targets(g, me, t, PT(ex, ey), pts);
       if (n > 0) {
         shuffle(g, pts, n);
+        #pragma unroll 1
         for (int i = 0; i < n && i < p[0]; i++) { tid = need(g, pts[i]); if (tid < 0) return; v_heal(g, tid, e.dmg); }
       }
       break;
@@ -616,6 +666,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       int c = count_types_friendly(g);
       t = mkT(TK_UNIT, TS_ENEMY);
       n = surrounding(g, ex, ey, CUR(g), &t, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) {
         tid = need(g, pts[i]);
         if (tid < 0) return;
@@ -637,6 +688,7 @@ SBD_NI void spell_effect(G& g, int card, int caster, int pos_pt) {
     case SBC_S003:  // cards/s003.py:14-19: ability_max_damage, ability_min_damage
       t = mkT(TK_ANY, TS_ENEMY);
       n = get_targets(g, CUR(g), t, PT_NONE, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) {
         if (need(g, pts[i]) < 0) return;
         deal_damage_pt(g, pts[i], p[1] + rng_below(g, p[0] + 1 - p[1]), 1);
@@ -650,6 +702,7 @@ SBD_NI void spell_effect(G& g, int card, int caster, int pos_pt) {
       if (ne > 0) {
         shuffle(g, em, ne);
         int amount = p[1] + rng_below(g, p[0] + 1 - p[1]);
+        #pragma unroll 1
         for (int i = 0; i < ne && i < amount; i++) spawn_token_unit(g, caster, em[i], 1, UT_TOAD);
       }
       break; }
@@ -667,13 +720,16 @@ SBD_NI void spell_effect(G& g, int card, int caster, int pos_pt) {
     case SBC_S013: {  // cards/s013.py:13-27
       i8 chosen[16]; int nc = 0;
       u32 taken = 0;
+      #pragma unroll 1
       for (int ut = 0; ut < 16; ut++) {
         t = mkT(TK_UNIT, TS_ANY); t.types = (u16)(1u << ut);
         n = get_targets(g, CUR(g), t, PT_NONE, pts);
         i8 units[22]; int nu = 0;
+        #pragma unroll 1
         for (int i = 0; i < n; i++) if (!(taken >> pts[i] & 1)) units[nu++] = pts[i];
         if (nu > 0) { int c = choice_pt(g, units, nu); chosen[nc++] = (i8)c; taken |= 1u << c; }
       }
+      #pragma unroll 1
       for (int i = 0; i < nc; i++) { deal_damage_pt(g, chosen[i], p[0], 1); if (g.err) return; }
       break; }
     case SBC_S021:  // cards/s021.py:13-25
@@ -684,7 +740,9 @@ SBD_NI void spell_effect(G& g, int card, int caster, int pos_pt) {
       n = get_targets(g, CUR(g), t, PT_NONE, pts);
       if (n > 0) {
         int mn = 32767; i8 wk[22]; int nw = 0;
+        #pragma unroll 1
         for (int i = 0; i < n; i++) { int s = g.e[at_pt(g, pts[i])].strength; if (s < mn) mn = s; }
+        #pragma unroll 1
         for (int i = 0; i < n; i++) if (g.e[at_pt(g, pts[i])].strength == mn) wk[nw++] = pts[i];
         tid = need(g, choice_pt(g, wk, nw));
         if (tid >= 0) v_heal(g, tid, p[0]);
@@ -696,6 +754,7 @@ SBD_NI void spell_effect(G& g, int card, int caster, int pos_pt) {
       n = get_targets(g, CUR(g), t, PT_NONE, pts);
       if (n == 0) { GERR(g, SB_ERR_INDEX); return; }
       i16 ks[22];
+      #pragma unroll 1
       for (int i = 0; i < n; i++) ks[i] = g.e[at_pt(g, pts[i])].strength;
       keyed_sort(g, pts, ks, n, false);
       tid = need(g, pts[0]);
@@ -715,22 +774,27 @@ SBD_NI void spell_effect(G& g, int card, int caster, int pos_pt) {
       u32 seen = 0;
       t = mkT(TK_UNIT, TS_FRIENDLY);
       int nf = get_targets(g, CUR(g), t, PT_NONE, fr);
+      #pragma unroll 1
       for (int i = 0; i < nf; i++) {
         Target te = mkT(TK_ANY, TS_ENEMY); te.base = 1;
         n = surrounding(g, PTX(fr[i]), PTY(fr[i]), CUR(g), &te, pts);
+        #pragma unroll 1
         for (int k = 0; k < n; k++) if (!(seen >> pts[k] & 1)) { seen |= 1u << pts[k]; all[na++] = pts[k]; }
       }
+      #pragma unroll 1
       for (int i = 0; i < na; i++) { deal_damage_pt(g, all[i], p[0], 1); if (g.err) return; }
       break; }
     case SBC_S302:  // cards/s302.py:14-22: ability_damage, ability_targets
       t = mkT(TK_ANY, TS_ENEMY); t.base = 1;
       n = get_targets(g, CUR(g), t, PT_NONE, pts);
       shuffle(g, pts, n);
+      #pragma unroll 1
       for (int i = 0; i < n && i < p[1]; i++) { deal_damage_pt(g, pts[i], p[0], 1); if (g.err) return; }
       break;
     case SBC_S403:  // cards/s403.py:13-22
       t = mkT(TK_UNIT, TS_FRIENDLY); t.status = 1 << SB_ST_POISONED;
       n = get_targets(g, CUR(g), t, PT_NONE, pts);
+      #pragma unroll 1
       for (int i = 0; i < n; i++) { tid = need(g, pts[i]); if (tid < 0) return; v_heal(g, tid, p[0]); v_vitalize(g, tid); }
       break;
     default: break;

@@ -126,6 +126,9 @@ SBD_FI void philox(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32& o0, u32&
   }
   o0 = c0; o1 = c1;
 }
+// one out-of-line IEEE FP64 division (each inline expansion is ~30 instructions of Newton iteration; the
+// rollout kernels are instruction-fetch bound, so code size matters more than a call)
+SBD_NI double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 SBD_NI int rng_below(G& g, int n) {
   if (n <= 0) { GERR(g, SB_ERR_EMPTY_CHOICE); return 0; }
   u32 w0, w1;
@@ -141,6 +144,7 @@ SBD_NI double rng_random(G& g) {
   return __dmul_rn(__dadd_rn(__dmul_rn((double)(w0 >> 5), 67108864.0), (double)(w1 >> 6)), 0x1.0p-53);
 }
 SBD void shuffle(G& g, i8* a, int n) {
+  #pragma unroll 1
   for (int i = n - 1; i > 0; i--) {
     int j = rng_below(g, i + 1);
     i8 t = a[i]; a[i] = a[j]; a[j] = t;
@@ -174,6 +178,7 @@ SBD_NI void calc_front_line(G& g, int order) {  // board.py:78-92
   const bool local = order == g.local_order;
   int fl = local ? 4 : 0;
   u32 m = g.occ;
+  #pragma unroll 1
   while (m) {
     int t = next_tile(m, local);
     if (ent_owner(g.e[g.board[t]]) == order) { int y = t >> 2; fl = local ? (y > 1 ? y : 1) : (y < 3 ? y : 3); break; }
@@ -226,6 +231,7 @@ SBD_NI int get_targets_region(const G& g, int pov, const Target& t, int exclude_
   bool pov_local = (pov == g.local_order);
   u32 m = g.occ & region;
   if ((unsigned)exclude_pt < 20u) m &= ~(1u << exclude_pt);
+  #pragma unroll 1
   while (m) {
     int tile = next_tile(m, pov_local);
     if (ent_matches(g, g.e[g.board[tile]], pov, t)) out[n++] = (i8)tile;
@@ -273,6 +279,7 @@ SBD_FI int border_list(int x, int y, i8* out) {
 }
 SBD_FI int surround_list(int x, int y, i8* out) {
   int n = 0;
+  #pragma unroll 1
   for (int dx = -1; dx <= 1; dx += 2) {
     int xx = x + dx;
     if (xx < 0 || xx > 3) continue;
@@ -286,9 +293,11 @@ SBD_FI int surround_list(int x, int y, i8* out) {
 }
 
 SBD_FI void sort_pts_by_y(i8* a, int n, bool desc) {  // stable insertion sort on Point.y (board.py:217,232)
+  #pragma unroll 1
   for (int i = 1; i < n; i++) {
     i8 v = a[i];
     int j = i - 1;
+    #pragma unroll 1
     while (j >= 0 && (desc ? PTY(a[j]) < PTY(v) : PTY(a[j]) > PTY(v))) { a[j + 1] = a[j]; j--; }
     a[j + 1] = v;
   }
@@ -437,6 +446,7 @@ SBD_NI void set_path(G& g, int id, int on_play, int extra_movement) {  // unit.p
   bool is_local = owner == g.local_order;
   int steps = on_play ? CARD(g, e.card).movement + extra_movement : 1;
   if (steps > MAXPATH) { GERR(g, SB_ERR_OVERFLOW); steps = MAXPATH; }
+  #pragma unroll 1
   for (int i = 0; i < steps; i++) {
     int dx = px, dy = py + (is_local ? -1 : 1);
     if (confused_cached > 0) {
@@ -454,6 +464,7 @@ SBD_NI void set_path(G& g, int id, int on_play, int extra_movement) {  // unit.p
         u8 lenc = enc_xy(px - 1, py), renc = enc_xy(px + 1, py);
         bool left_ok = left >= 0 && ent_owner(g.e[left]) != owner;
         bool right_ok = right >= 0 && ent_owner(g.e[right]) != owner;
+        #pragma unroll 1
         for (int k = 0; k < nd; k++) { if (dest[k] == lenc) left_ok = false; if (dest[k] == renc) right_ok = false; }
         if (px <= 1) { if (right_ok) { dx = px + 1; dy = py; } else if (left_ok) { dx = px - 1; dy = py; } }
         else { if (left_ok) { dx = px - 1; dy = py; } else if (right_ok) { dx = px + 1; dy = py; } }
@@ -462,6 +473,7 @@ SBD_NI void set_path(G& g, int id, int on_play, int extra_movement) {  // unit.p
     dest[nd++] = enc_xy(dx, dy);
     px = dx; py = dy;
   }
+  #pragma unroll 1
   for (int i = 0; i < nd; i++) e.path[i] = dest[i];
   e.path_len = (u8)nd;
 }
@@ -482,7 +494,9 @@ SBD_NI void unit_move(G& g, int id) {  // unit.py:124-203
   if (e.st[SB_ST_FROZEN]) { g.depth--; return; }
   u8 path[MAXPATH];
   const int np = e.path_len;  // `for destination in self.path` iterates the list object bound now
+  #pragma unroll 1
   for (int i = 0; i < np; i++) path[i] = e.path[i];
+  #pragma unroll 1
   for (int i = 0; i < np; i++) {
     const int dx = path[i] & 3, dy = (path[i] >> 2) - 1;
     const int owner = ent_owner(e);
@@ -555,6 +569,7 @@ SBD_NI void v_push(G& g, int id, int fx, int fy) {  // unit.py:318-339
   int dx = 0, dy = 0;
   if (fy < e.y) dy = 1; else if (fy > e.y) dy = -1; else if (fx < e.x) dx = 1; else if (fx > e.x) dx = -1;
   if (dx || dy) {
+    #pragma unroll 1
     for (;;) {
       int nx = e.x + dx, ny = e.y + dy;
       if (!valid_xy(nx, ny)) break;
@@ -574,12 +589,14 @@ SBD_NI void v_force_attack(G& g, int id, int tx, int ty) {  // unit.py:341-371
   bool vertical = (tx == e.x);
   int fixed = vertical ? e.x : e.y, start = vertical ? e.y : e.x, end = vertical ? ty : tx;
   int delta = end > start ? 1 : -1;
+  #pragma unroll 1
   for (int i = start + delta; i != end + delta; i += delta) {
     int x = vertical ? fixed : i, y = vertical ? i : fixed;
     if (i != end && at_xy(g, x, y) >= 0) return;
     dest[nd++] = enc_xy(x, y);
   }
   if (nd > 0) {
+    #pragma unroll 1
     for (int i = 0; i < nd; i++) e.path[i] = dest[i];
     e.path_len = (u8)nd;
     unit_move(g, id);
@@ -604,6 +621,7 @@ SBD_NI void v_teleport(G& g, int id, int dx, int dy) {  // unit.py:373-382
 SBD_NI int first_equal(G& g, const CardRec* l, int n, int idx) {
   const CardRec t = l[idx];
   if (CARD(g, t.card).kind == KIND_SPELL) return idx;
+  #pragma unroll 1
   for (int i = 0; i < idx && i < n; i++) {
     if (l[i].card != t.card) continue;
     int oi = l[i].flags & SB_CF_OBJ, ot = t.flags & SB_CF_OBJ;
@@ -614,14 +632,17 @@ SBD_NI int first_equal(G& g, const CardRec* l, int n, int idx) {
 }
 SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + numpy choice(p=) semantics
   Ply& p = g.pl[order];
+  #pragma unroll 1
   for (int k = 0; k < amount; k++) {
     int n = p.n_deck;
     if (n <= 0) { GERR(g, SB_ERR_EMPTY_CHOICE); return; }
     double sum = 0.0;
+    #pragma unroll 1
     for (int i = 0; i < n; i++) sum = __dadd_rn(sum, __ldg(&g.wt[p.deck[i].wn]));
     double cdf[DECK_W];
     double acc = 0.0;
-    for (int i = 0; i < n; i++) { acc = __dadd_rn(acc, __ddiv_rn(__ldg(&g.wt[p.deck[i].wn]), sum)); cdf[i] = acc; }
+    #pragma unroll 1
+    for (int i = 0; i < n; i++) { acc = __dadd_rn(acc, ddiv(__ldg(&g.wt[p.deck[i].wn]), sum)); cdf[i] = acc; }
     double last = cdf[n - 1];
     double u = rng_random(g);
     // idx = #{i : fl(cdf_i / last) <= u} (searchsorted side='right' on the normalised cdf).  Rounding is
@@ -630,9 +651,10 @@ SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + num
     const double t = __dmul_rn(u, last);
     const double t_lo = __dmul_rn(t, 0.999999999999999), t_hi = __dmul_rn(t, 1.000000000000001);
     int idx = 0;
+    #pragma unroll 1
     for (int i = 0; i < n; i++) {
       const double c = cdf[i];
-      if (c < t_lo || (c <= t_hi && __ddiv_rn(c, last) <= u)) idx++;
+      if (c < t_lo || (c <= t_hi && ddiv(c, last) <= u)) idx++;
     }
     if (idx > n - 1) idx = n - 1;
     CardRec c = p.deck[idx];
@@ -641,6 +663,7 @@ SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + num
     p.hand[p.n_hand++] = c;
     int j = first_equal(g, p.deck, n, idx);
     if (j != idx) p.deck[idx].wn = 0;
+    #pragma unroll 1
     for (int i = j; i < n - 1; i++) p.deck[i] = p.deck[i + 1];
     p.n_deck--;
   }
@@ -648,9 +671,11 @@ SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + num
 SBD_FI void player_fill_hand(G& g, int order) { player_draw(g, order, 4 - g.pl[order].n_hand); }
 SBD_NI void player_discard(G& g, int order, int index) {  // player.py:57-66
   Ply& p = g.pl[order];
+  #pragma unroll 1
   for (int i = 0; i < p.n_deck; i++) { if (p.deck[i].wn >= WT_N - 1) GERR(g, SB_ERR_OVERFLOW); else p.deck[i].wn++; }
   CardRec target = p.hand[index];
   int j = first_equal(g, p.hand, p.n_hand, index);
+  #pragma unroll 1
   for (int i = j; i < p.n_hand - 1; i++) p.hand[i] = p.hand[i + 1];
   p.n_hand--;
   if (!(target.flags & SB_CF_SINGLE_USE)) {
@@ -665,6 +690,7 @@ SBD_NI void player_play(G& g, int order, int index, int pos_pt) {  // player.py:
   CardRec target = p.hand[index];
   if (g.hist_n < 4) { g.hist_card[g.hist_n] = target.card; g.hist_owner[g.hist_n] = (u8)order; g.hist_n++; }
   else {
+    #pragma unroll 1
     for (int i = 0; i < 3; i++) { g.hist_card[i] = g.hist_card[i + 1]; g.hist_owner[i] = g.hist_owner[i + 1]; }
     g.hist_card[3] = target.card; g.hist_owner[3] = (u8)order;
   }
@@ -677,6 +703,7 @@ SBD_NI void player_play(G& g, int order, int index, int pos_pt) {  // player.py:
       Target t = card_target(c);
       int n = get_targets(g, g.current_order, t, PT_NONE, tg);
       ok = false;
+      #pragma unroll 1
       for (int i = 0; i < n; i++) if (tg[i] == pos_pt) ok = true;
     }
     if (ok) spell_ability(g, target.card, order, pos_pt);
@@ -698,9 +725,11 @@ SBD_NI void board_flip(G& g) {  // board.py:94-115
   g.local_order ^= 1;
   g.pl[0].front_line = (i8)(4 - g.pl[0].front_line);
   g.pl[1].front_line = (i8)(4 - g.pl[1].front_line);
+  #pragma unroll 1
   for (int t = 0; t < 10; t++) { i8 a = g.board[t]; g.board[t] = g.board[19 - t]; g.board[19 - t] = a; }
   g.occ = (__brev(g.occ) >> 12);  // tile t -> 19 - t
   u32 m = g.occ;
+  #pragma unroll 1
   while (m) { int t = next_tile(m, true); int id = g.board[t]; g.e[id].x = (u8)(t & 3); g.e[id].y = (u8)(t >> 2); }
 }
 SBD_NI void to_next_turn(G& g) {  // board.py:117-145
@@ -720,12 +749,16 @@ SBD_NI void to_next_turn(G& g) {  // board.py:117-145
   g.pl[g.current_order].leftmost = 1;
   Target ts = mkT(TK_STRUCTURE, TS_FRIENDLY);
   n = get_targets(g, g.current_order, ts, PT_NONE, pts);
+  #pragma unroll 1
   for (int i = 0; i < n; i++) ids[i] = (i8)at_pt(g, pts[i]);
+  #pragma unroll 1
   for (int i = 0; i < n; i++)
     if (CARD(g, g.e[ids[i]].card).trigger == TR_TURN_START) ability(g, ids[i], PT(g.e[ids[i]].x, g.e[ids[i]].y), 1);
   Target tu = mkT(TK_UNIT, TS_FRIENDLY);
   n = get_targets(g, g.current_order, tu, PT_NONE, pts);
+  #pragma unroll 1
   for (int i = 0; i < n; i++) ids[i] = (i8)at_pt(g, pts[i]);
+  #pragma unroll 1
   for (int i = 0; i < n; i++) { set_path(g, ids[i], 0, 0); unit_move(g, ids[i]); }  // snapshot incl. ghosts (Q21)
   g.phase = PH_PLAY;
 }
@@ -743,6 +776,7 @@ SBD_NI int legal_mask(const G& g, u32* m) {
   const int fl = p.front_line < 1 ? 1 : p.front_line;
   empty16 &= fl > 4 ? 0u : (0xFFFFu >> ((fl - 1) * 4));
   int n_empty = __popc(empty16);
+  #pragma unroll 1
   for (int ci = 0; ci < p.n_hand && ci < SB_HAND_MAX; ci++) {
     const DCard& c = CARD(g, p.hand[ci].card);
     if (p.hand[ci].cost > p.mana) continue;
@@ -756,6 +790,7 @@ SBD_NI int legal_mask(const G& g, u32* m) {
       i8 tg[24];
       Target t = card_target(c);
       int nt = get_targets(g, g.current_order, t, PT_NONE, tg);
+      #pragma unroll 1
       for (int i = 0; i < nt; i++) {
         if (is_base_pt(tg[i])) continue;
         mask_set(m, 65 + 21 * ci + (4 - PTY(tg[i])) * 4 + PTX(tg[i])); n_play++;
@@ -823,32 +858,39 @@ SBD_FI void end_of_step(G& g) {
 }
 SBD_NI void compact(G& g) {
   u8 remap[MAXE];
+  #pragma unroll 1
   for (int i = 0; i < g.n_ent; i++) remap[i] = 0xFF;
   Ent tmp[SB_N_TILES];
   int n = 0;
+  #pragma unroll 1
   for (int t = 0; t < 20; t++) {
     int id = g.board[t];
     if (id < 0) continue;
     remap[id] = (u8)n;
     tmp[n] = g.e[id];
     tmp[n].path_len = 0; tmp[n].move_id = 0; tmp[n].dmg = 0; tmp[n].fl &= ~(EF_RPLAY | EF_SINGLE);
+    #pragma unroll 1
     for (int k = 0; k < 5; k++) if (tmp[n].st[k] > 63) tmp[n].st[k] = 63;
     g.board[t] = (i8)n;
     n++;
   }
   // frozen strength of board-instance card records whose object left the board
+  #pragma unroll 1
   for (int o = 0; o < 2; o++) {
     Ply& p = g.pl[o];
+    #pragma unroll 1
     for (int i = 0; i < p.n_hand; i++) if (p.hand[i].link >= 0) {
       u8 r = remap[p.hand[i].link];
       if (r == 0xFF) { p.hand[i].xstr = g.e[p.hand[i].link].strength; p.hand[i].link = -1; } else p.hand[i].link = (i8)r;
     }
+    #pragma unroll 1
     for (int i = 0; i < p.n_deck; i++) if (p.deck[i].link >= 0) {
       u8 r = remap[p.deck[i].link];
       if (r == 0xFF) { p.deck[i].xstr = g.e[p.deck[i].link].strength; p.deck[i].link = -1; } else p.deck[i].link = (i8)r;
     }
   }
   int w = 0;
+  #pragma unroll 1
   for (int i = 0; i < g.n_mem; i++) {
     if (g.mem[i].b005 < 0) continue;
     u8 r = remap[g.mem[i].b005];
@@ -858,12 +900,16 @@ SBD_NI void compact(G& g) {
   g.n_mem = (u8)w;
   // what would not fit the packed layout is an overflow there too (keeps rollouts == step-per-launch)
   int nobj = 0;
+  #pragma unroll 1
   for (int o = 0; o < 2; o++) {
+    #pragma unroll 1
     for (int i = 0; i < g.pl[o].n_hand; i++) nobj += (g.pl[o].hand[i].flags & SB_CF_OBJ) != 0;
+    #pragma unroll 1
     for (int i = 0; i < g.pl[o].n_deck; i++) nobj += (g.pl[o].deck[i].flags & SB_CF_OBJ) != 0;
   }
   if (w > NMEM_PACKED || nobj > NOBJ_PACKED) GERR(g, SB_ERR_OVERFLOW);
   g.n_obj = (u8)(nobj > 255 ? 255 : nobj);
+  #pragma unroll 1
   for (int i = 0; i < n; i++) g.e[i] = tmp[i];
   g.n_ent = (u8)n;
   g.n_trig = 0; g.resolving = 0; g.depth = 0;

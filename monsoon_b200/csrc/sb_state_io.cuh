@@ -27,21 +27,25 @@ SBD_NI void unpack(G& g, const SbState& s) {
 #pragma unroll
   for (int i = 0; i < 4; i++) { g.hist_card[i] = s.hist_card[i]; g.hist_owner[i] = s.hist_owner[i]; }
   g.n_ent = 0; g.n_trig = 0; g.resolving = 0; g.depth = 0; g.n_mem = 0; g.n_obj = 0; g.occ = 0;
+  #pragma unroll 1
   for (int o = 0; o < 2; o++) {
     const SbPlayer& sp = s.pl[o];
     Ply& p = g.pl[o];
     p.base = sp.base; p.max_mana = sp.max_mana; p.mana = sp.mana; p.front_line = sp.front_line;
     p.replacable = (sp.flags & SB_PF_REPLACABLE) != 0; p.leftmost = (sp.flags & SB_PF_LEFTMOST) != 0;
     p.n_hand = sp.n_hand; p.n_deck = sp.n_deck; p.faction = sp.faction;
+    #pragma unroll 1
     for (int i = 0; i < SB_HAND_MAX; i++) {
       CardRec& c = p.hand[i];
       c.card = sp.hand_card[i]; c.cost = sp.hand_cost[i]; c.flags = sp.hand_flags[i]; c.link = -1; c.wn = 0; c.xstr = 0;
     }
+    #pragma unroll 1
     for (int i = 0; i < SB_DECK_MAX; i++) {
       CardRec& c = p.deck[i];
       c.card = sp.deck_card[i]; c.cost = sp.deck_cost[i]; c.flags = sp.deck_flags[i]; c.link = -1; c.wn = sp.deck_wn[i]; c.xstr = 0;
     }
   }
+  #pragma unroll 1
   for (int t = 0; t < SB_N_TILES; t++) {
     const SbTile& st = s.tile[t];
     g.board[t] = -1;
@@ -60,6 +64,7 @@ SBD_NI void unpack(G& g, const SbState& s) {
   }
   const u8* x = s.ext;
   int nm = x[0];
+  #pragma unroll 1
   for (int i = 0; i < nm && i < NMEM_PACKED; i++) {
     const u8* r = x + 1 + 10 * i;
     Mem& m = g.mem[g.n_mem++];
@@ -73,6 +78,7 @@ SBD_NI void unpack(G& g, const SbState& s) {
   }
   int no = x[91];
   g.n_obj = (u8)no;
+  #pragma unroll 1
   for (int i = 0; i < no && i < NOBJ_PACKED; i++) {
     const u8* r = x + 92 + 4 * i;
     Ply& p = g.pl[r[0] >> 7];
@@ -93,6 +99,7 @@ SBD_NI void pack(const G& g, SbState& s) {
   s.phase = g.phase; s.err = g.err; s.done = g.done; s.hist_n = g.hist_n;
 #pragma unroll
   for (int i = 0; i < 4; i++) { s.hist_card[i] = g.hist_card[i]; s.hist_owner[i] = g.hist_owner[i]; }
+  #pragma unroll 1
   for (int o = 0; o < 2; o++) {
     SbPlayer& sp = s.pl[o];
     const Ply& p = g.pl[o];
@@ -104,9 +111,12 @@ SBD_NI void pack(const G& g, SbState& s) {
       if (p.n_hand > SB_HAND_MAX) sp.n_hand = SB_HAND_MAX;
       if (p.n_deck > SB_DECK_MAX) sp.n_deck = SB_DECK_MAX;
     }
+    #pragma unroll 1
     for (int i = 0; i < p.n_hand && i < SB_HAND_MAX; i++) { sp.hand_card[i] = p.hand[i].card; sp.hand_cost[i] = p.hand[i].cost; sp.hand_flags[i] = p.hand[i].flags; }
+    #pragma unroll 1
     for (int i = 0; i < p.n_deck && i < SB_DECK_MAX; i++) { sp.deck_card[i] = p.deck[i].card; sp.deck_cost[i] = p.deck[i].cost; sp.deck_flags[i] = p.deck[i].flags; sp.deck_wn[i] = p.deck[i].wn; }
   }
+  #pragma unroll 1
   for (int t = 0; t < SB_N_TILES; t++) {
     int id = g.board[t];
     if (id < 0) continue;
@@ -124,9 +134,11 @@ SBD_NI void pack(const G& g, SbState& s) {
   }
   u8* x = s.ext;
   int nm = 0;
+  #pragma unroll 1
   for (int tile = 0; tile < SB_N_TILES; tile++) {  // canonical order: temples in tile order, copies in memory order
     int bid = g.board[tile];
     if (bid < 0 || g.e[bid].card != SBC_B005) continue;
+    #pragma unroll 1
     for (int i = 0; i < g.n_mem; i++) {
       const Mem& m = g.mem[i];
       if (m.b005 != bid) continue;
@@ -142,9 +154,11 @@ SBD_NI void pack(const G& g, SbState& s) {
   }
   x[0] = (u8)nm;
   int no = 0;
+  #pragma unroll 1
   for (int o = 0; o < 2; o++) for (int where = 0; where < 2; where++) {
     const Ply& p = g.pl[o];
     int cnt = where ? p.n_deck : p.n_hand;
+    #pragma unroll 1
     for (int i = 0; i < cnt; i++) {
       const CardRec& c = where ? p.deck[i] : p.hand[i];
       if (!(c.flags & SB_CF_OBJ)) continue;
@@ -163,6 +177,7 @@ SBD_NI void pack(const G& g, SbState& s) {
 SBD_FI unsigned long long digest_state(const SbState& s) {  // FNV-1a 64 over the 512 bytes
   const u8* b = reinterpret_cast<const u8*>(&s);
   unsigned long long h = 0xCBF29CE484222325ull;
+  #pragma unroll 1
   for (int i = 0; i < SB_STATE_BYTES; i++) { h ^= b[i]; h *= 0x100000001B3ull; }
   return h;
 }
@@ -187,11 +202,12 @@ SBD_NI int features(const G& g, double* f) {
   double est = __dadd_rn(m, 2.0);
   if (est < 3.0) est = 3.0;
   if (est > 10.0) est = 10.0;
-  f[0] = clip01(__dsub_rn(1.0, __ddiv_rn(m, est)));
+  f[0] = clip01(__dsub_rn(1.0, ddiv(m, est)));
   f[1] = __dsub_rn(hl, hr);
   long long sl = 0, sr = 0;
   int nl = 0, nr = 0, nsl = 0, nsr = 0, minl = 99, maxr = -1;
   double threat = 0.0, prot = 0.0;
+  #pragma unroll 1
   for (int t = 0; t < SB_N_TILES; t++) {
     int id = g.board[t];
     if (id < 0) continue;
@@ -202,18 +218,18 @@ SBD_NI int features(const G& g, double* f) {
     const bool counted = e.strength != -1;
     if (ent_owner(e) == lo) {
       if (!ent_struct(e)) { nl++; if (y < minl) minl = y; } else nsl++;
-      if (counted) { sl += e.strength; prot = __dadd_rn(prot, __dmul_rn((double)e.strength, __ddiv_rn((double)(5 - y), 5.0))); }
+      if (counted) { sl += e.strength; prot = __dadd_rn(prot, __dmul_rn((double)e.strength, ddiv((double)(5 - y), 5.0))); }
     } else {
       if (!ent_struct(e)) {
         nr++; if (y > maxr) maxr = y;
-        if (counted) threat = __dadd_rn(threat, __dmul_rn((double)e.strength, __ddiv_rn((double)(y + 1), 5.0)));
+        if (counted) threat = __dadd_rn(threat, __dmul_rn((double)e.strength, ddiv((double)(y + 1), 5.0)));
       } else nsr++;
       if (counted) sr += e.strength;
     }
   }
   long long tot = sl + sr;
-  f[2] = tot == 0 ? 0.0 : __ddiv_rn((double)(sl - sr), (double)tot);
-  f[3] = (nl == 0 && nr == 0) ? 0.0 : __ddiv_rn((double)((nr ? maxr : 0) - (nl ? minl : 4)), 4.0);
+  f[2] = tot == 0 ? 0.0 : ddiv((double)(sl - sr), (double)tot);
+  f[3] = (nl == 0 && nr == 0) ? 0.0 : ddiv((double)((nr ? maxr : 0) - (nl ? minl : 4)), 4.0);
   f[4] = (double)(sl - sr);
   f[5] = (double)(nl - nr);
   f[6] = (double)(nsl - nsr);
@@ -221,6 +237,7 @@ SBD_NI int features(const G& g, double* f) {
   f[8] = prot;
   int playable = 0, valid = 0;
   double total = 0.0;
+  #pragma unroll 1
   for (int i = 0; i < L.n_hand && i < 4; i++) {
     const DCard& c = CARD(g, L.hand[i].card);
     if (c.obs_id == -32768) err = SB_ERR_OBS_ID;
@@ -230,17 +247,19 @@ SBD_NI int features(const G& g, double* f) {
     if (str == -1) str = 0;
     valid++;
     if (cost > 0) {
-      total = __dadd_rn(total, __ddiv_rn((double)str, (double)cost));
+      total = __dadd_rn(total, ddiv((double)str, (double)cost));
       if ((double)cost <= m) playable++;
     }
   }
   if (valid == 0) f[9] = 0.0;
   else {
-    double playability = __ddiv_rn((double)playable, (double)valid);
-    double avg = __ddiv_rn(total, (double)valid);
-    f[9] = __ddiv_rn(__dadd_rn(playability, clip01(__ddiv_rn(avg, 3.0))), 2.0);
+    double playability = ddiv((double)playable, (double)valid);
+    double avg = ddiv(total, (double)valid);
+    f[9] = ddiv(__dadd_rn(playability, clip01(ddiv(avg, 3.0))), 2.0);
   }
+  #pragma unroll 1
   for (int i = 0; i < L.n_deck; i++) if (CARD(g, L.deck[i].card).obs_id == -32768) err = SB_ERR_OBS_ID;
+  #pragma unroll 1
   for (int i = 0; i < g.hist_n; i++) if (CARD(g, g.hist_card[i]).obs_id == -32768) err = SB_ERR_OBS_ID;
   return err;
 }
@@ -257,8 +276,10 @@ SBD_FI void obs_card_row(const G& g, int* obs, int layer, int row, const CardRec
 }
 SBD_NI int observe(const G& g, int* obs) {
   int err = 0;
+  #pragma unroll 1
   for (int i = 0; i < SB_OBS_INTS; i++) obs[i] = -1;
   const int lo = g.local_order;
+  #pragma unroll 1
   for (int t = 0; t < SB_N_TILES; t++) {
     int id = g.board[t];
     if (id < 0) continue;
@@ -279,26 +300,36 @@ SBD_NI int observe(const G& g, int* obs) {
   }
   const Ply& L = g.pl[lo];
   const Ply& R = g.pl[1 - lo];
+  #pragma unroll 1
   for (int i = 0; i < L.n_hand && i < 4; i++) obs_card_row(g, obs, 6, i, L.hand[i], err);
+  #pragma unroll 1
   for (int c = 0; c < 4; c++) OBSI(6, 4, c) = 32767;
   u8 idx[SB_DECK_MAX];
+  #pragma unroll 1
   for (int i = 0; i < L.n_deck; i++) idx[i] = (u8)i;
+  #pragma unroll 1
   for (int i = 1; i < L.n_deck; i++) {  // sorted(deck, key=(cost, card_id)), stable
     u8 v = idx[i];
     int j = i - 1;
+    #pragma unroll 1
     while (j >= 0 && (L.deck[idx[j]].cost > L.deck[v].cost ||
                       (L.deck[idx[j]].cost == L.deck[v].cost && L.deck[idx[j]].card > L.deck[v].card))) { idx[j + 1] = idx[j]; j--; }
     idx[j + 1] = v;
   }
+  #pragma unroll 1
   for (int layer = 0; layer < 6; layer++) {
+    #pragma unroll 1
     for (int k = 0; k < 4; k++) { int d = layer * 4 + k; if (d < L.n_deck) obs_card_row(g, obs, 7 + layer, k, L.deck[idx[d]], err); }
+    #pragma unroll 1
     for (int c = 0; c < 4; c++) OBSI(7 + layer, 4, c) = 32768;
   }
+  #pragma unroll 1
   for (int r = 0; r < 5; r++) for (int c = 0; c < 4; c++) {
     OBSI(13, r, c) = L.mana; OBSI(14, r, c) = L.base; OBSI(15, r, c) = L.faction;
     OBSI(22, r, c) = R.mana; OBSI(23, r, c) = R.base; OBSI(24, r, c) = R.faction;
     OBSI(25, r, c) = g.player_sign * 99999;
   }
+  #pragma unroll 1
   for (int i = 0; i < 4; i++) {
     int h = i - (4 - g.hist_n);
     if (h >= 0) {
@@ -307,6 +338,7 @@ SBD_NI int observe(const G& g, int* obs) {
       if (CARD(g, g.hist_card[h]).obs_id == -32768) err = SB_ERR_OBS_ID;
     }
   }
+  #pragma unroll 1
   for (int c = 0; c < 4; c++) OBSI(26, 4, c) = 32769;
   return err;
 }
