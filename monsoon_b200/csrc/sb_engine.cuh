@@ -97,6 +97,8 @@ struct G {
   u8 n_ent, n_trig, resolving, depth, n_mem;
   u8 n_obj;   // card records that are board instances of B305 (SB_CF_OBJ); 0 on the fast path
   u32 occ;    // occupied-tile bitmask, mirrors board[]
+  u32 own1;   // occupied tiles whose entity belongs to order 1 (bits of empty tiles are don't-care)
+  u32 strc;   // occupied tiles holding a structure (bits of empty tiles are don't-care)
   u8 trig[MAXTRIG];  // entity id | has_source << 7
   Mem mem[NMEM];
   const DCard* cards;   // shared-memory copy
@@ -164,8 +166,17 @@ SBD_FI int at_pt(const G& g, int pt) { return (unsigned)pt < 20u ? g.board[pt] :
 // every board scan walks the set bits only (a board holds ~6 entities, not 20).
 SBD_FI void set_xy(G& g, int x, int y, int id) {
   const int t = y * 4 + x;
+  const u32 b = 1u << t;
   g.board[t] = (i8)id;
-  if (id >= 0) { g.e[id].x = (u8)x; g.e[id].y = (u8)y; g.occ |= 1u << t; } else g.occ &= ~(1u << t);
+  if (id >= 0) {
+    Ent& e = g.e[id];
+    e.x = (u8)x; e.y = (u8)y;
+    g.occ |= b;
+    g.own1 = (e.fl & EF_OWNER) ? (g.own1 | b) : (g.own1 & ~b);
+    g.strc = (e.fl & EF_STRUCT) ? (g.strc | b) : (g.strc & ~b);
+  } else {
+    g.occ &= ~b;
+  }
 }
 SBD_FI void clear_at(G& g, const Ent& e) { const int t = e.y * 4 + e.x; g.board[t] = -1; g.occ &= ~(1u << t); }
 // next tile of mask m in scan order: ascending (pov == local: y=0..4, x=0..3) or descending (board.py:157-158)
@@ -177,11 +188,10 @@ SBD_FI int next_tile(u32& m, bool ascending) {
 SBD_NI void calc_front_line(G& g, int order) {  // board.py:78-92
   const bool local = order == g.local_order;
   int fl = local ? 4 : 0;
-  u32 m = g.occ;
-  #pragma unroll 1
-  while (m) {
-    int t = next_tile(m, local);
-    if (ent_owner(g.e[g.board[t]]) == order) { int y = t >> 2; fl = local ? (y > 1 ? y : 1) : (y < 3 ? y : 3); break; }
+  const u32 m = g.occ & (order ? g.own1 : ~g.own1);  // this side's entities: first (local) / last (remote) occupied row
+  if (m) {
+    const int y = (local ? __ffs(m) - 1 : 31 - __clz(m)) >> 2;
+    fl = local ? (y > 1 ? y : 1) : (y < 3 ? y : 3);
   }
   g.pl[order].front_line = (i8)fl;
 }
@@ -197,44 +207,48 @@ SBD_FI Target card_target(const DCard& c) {
   t.has_limit = c.t_limit >= 0; t.limit = c.t_limit; t.nonhero = (c.flags & DCF_TNONHERO) != 0; t.base = (c.flags & DCF_TBASE) != 0;
   return t;
 }
-SBD_FI bool ent_matches(const G& g, const Ent& e, int pov, const Target& t) {
-  if (e.strength <= 0) return false;
-  bool strength_ok = !t.has_limit || e.strength <= t.limit;
-  bool kind_ok;
-  if (!ent_struct(e)) {
-    u16 types = CARD(g, e.card).types;
-    bool ok = strength_ok;
-    if (t.types && !(types & t.types)) ok = false;
-    if (t.xtypes && (types & t.xtypes)) ok = false;
-    if (t.nonhero && (types & (1 << UT_HERO))) ok = false;
-    if (t.status) {
-      bool any = false;
-#pragma unroll
-      for (int s = 0; s < 5; s++) if ((t.status >> s & 1) && e.st[s]) any = true;
-      ok = ok && any;
-    }
-    if (t.xstatus) {
-#pragma unroll
-      for (int s = 0; s < 5; s++) if ((t.xstatus >> s & 1) && e.st[s]) ok = false;
-    }
-    kind_ok = ok && t.kind != TK_STRUCTURE;
-  } else {
-    kind_ok = strength_ok && t.kind != TK_UNIT;
+// the rare filters of board.py:170-179 (side and kind are already decided by the bitmasks of the caller)
+SBD_NI bool ent_matches_filters(const G& g, const Ent& e, const Target& t) {
+  if (t.has_limit && e.strength > t.limit) return false;
+  if (ent_struct(e)) return true;  // structures only honour strength_limit (board.py:179)
+  u16 types = CARD(g, e.card).types;
+  if (t.types && !(types & t.types)) return false;
+  if (t.xtypes && (types & t.xtypes)) return false;
+  if (t.nonhero && (types & (1 << UT_HERO))) return false;
+  if (t.status) {
+    bool any = false;
+#pragma unroll 1
+    for (int s = 0; s < 5; s++) if ((t.status >> s & 1) && e.st[s]) any = true;
+    if (!any) return false;
   }
-  bool side_ok = t.side == TS_ANY || ((t.side == TS_FRIENDLY) == (ent_owner(e) == pov));
-  return kind_ok && side_ok;
+  if (t.xstatus) {
+#pragma unroll 1
+    for (int s = 0; s < 5; s++) if ((t.xstatus >> s & 1) && e.st[s]) return false;
+  }
+  return true;
 }
 // region = bitmask over tiles (bit t) that a tile must belong to; 0xFFFFF = whole board.
 // base_passes: base points survive the region filter when include_base (board.py:215,262,276,294).
 SBD_NI int get_targets_region(const G& g, int pov, const Target& t, int exclude_pt, u32 region, bool base_passes, i8* out) {
   int n = 0;
   bool pov_local = (pov == g.local_order);
+  // side and kind are decided by bitmask algebra (own1 = tiles whose entity belongs to order 1, strc =
+  // structure tiles); the per-entity loop only sees real candidates and usually checks strength > 0 alone
   u32 m = g.occ & region;
   if ((unsigned)exclude_pt < 20u) m &= ~(1u << exclude_pt);
+  if (t.side != TS_ANY) {
+    const u32 mine = pov ? g.own1 : ~g.own1;
+    m &= (t.side == TS_FRIENDLY) ? mine : ~mine;
+  }
+  if (t.kind == TK_UNIT) m &= ~g.strc; else if (t.kind == TK_STRUCTURE) m &= g.strc;
+  const bool filters = t.has_limit | t.nonhero | t.status | t.xstatus | (t.types != 0) | (t.xtypes != 0);
   #pragma unroll 1
   while (m) {
     int tile = next_tile(m, pov_local);
-    if (ent_matches(g, g.e[g.board[tile]], pov, t)) out[n++] = (i8)tile;
+    const Ent& e = g.e[g.board[tile]];
+    if (e.strength <= 0) continue;  // board.py:164
+    if (filters && !ent_matches_filters(g, e, t)) continue;
+    out[n++] = (i8)tile;
   }
   if (t.base && base_passes) {
     int friendly = pov_local ? PT_BASE_LOCAL : PT_BASE_REMOTE;
@@ -562,6 +576,10 @@ SBD_NI void v_convert(G& g, int id) {  // unit.py:291-293
   Ent& e = g.e[id];
   int o = opponent_of(g, ent_owner(e));
   e.fl = (u8)((e.fl & ~EF_OWNER) | (o ? EF_OWNER : 0));
+  if (g.board[e.y * 4 + e.x] == id) {  // keep the owner mask in step (a converted ghost is not on the board)
+    const u32 b = 1u << (e.y * 4 + e.x);
+    g.own1 = o ? (g.own1 | b) : (g.own1 & ~b);
+  }
   set_path(g, id, (e.fl & EF_RPLAY) != 0, 0);
 }
 SBD_NI void v_push(G& g, int id, int fx, int fy) {  // unit.py:318-339
@@ -728,6 +746,8 @@ SBD_NI void board_flip(G& g) {  // board.py:94-115
   #pragma unroll 1
   for (int t = 0; t < 10; t++) { i8 a = g.board[t]; g.board[t] = g.board[19 - t]; g.board[19 - t] = a; }
   g.occ = (__brev(g.occ) >> 12);  // tile t -> 19 - t
+  g.own1 = (__brev(g.own1) >> 12);
+  g.strc = (__brev(g.strc) >> 12);
   u32 m = g.occ;
   #pragma unroll 1
   while (m) { int t = next_tile(m, true); int id = g.board[t]; g.e[id].x = (u8)(t & 3); g.e[id].y = (u8)(t >> 2); }

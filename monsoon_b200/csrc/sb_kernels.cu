@@ -457,6 +457,17 @@ int sb_create(int device, SbHandle** out) {
   h->persistent = 0;
   h->turn_sync = 1;
   {
+    // shared-memory carveout: left to the driver by default.  Measured (tools/sweep_sync.py): forcing
+    // MaxL1 halves the saturated throughput (the 3 KB card table per CTA no longer fits 16 CTAs/SM).
+    const char* co = getenv("SB_CARVEOUT");
+    const int carve = co ? atoi(co) : 25;  // 25 % = 57 KB shared: fits 16 CTAs x 3 KB, leaves ~170 KB of L1 (+2-4 % measured vs driver default)
+    if (carve >= 0) {
+      CK(cudaFuncSetAttribute(k_rollout_random<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      CK(cudaFuncSetAttribute(k_rollout_random<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      CK(cudaFuncSetAttribute(k_rollout_heuristic, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      CK(cudaFuncSetAttribute(k_select_action, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      CK(cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+    }
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rollout_random<false>, TPB_GAME, 0));
     h->ctas_per_sm = nb > 0 ? nb : 8;

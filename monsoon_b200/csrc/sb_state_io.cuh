@@ -26,7 +26,7 @@ SBD_NI void unpack(G& g, const SbState& s) {
   g.phase = s.phase; g.err = s.err; g.done = s.done; g.hist_n = s.hist_n;
 #pragma unroll
   for (int i = 0; i < 4; i++) { g.hist_card[i] = s.hist_card[i]; g.hist_owner[i] = s.hist_owner[i]; }
-  g.n_ent = 0; g.n_trig = 0; g.resolving = 0; g.depth = 0; g.n_mem = 0; g.n_obj = 0; g.occ = 0;
+  g.n_ent = 0; g.n_trig = 0; g.resolving = 0; g.depth = 0; g.n_mem = 0; g.n_obj = 0; g.occ = 0; g.own1 = 0; g.strc = 0;
   #pragma unroll 1
   for (int o = 0; o < 2; o++) {
     const SbPlayer& sp = s.pl[o];
@@ -61,6 +61,8 @@ SBD_NI void unpack(G& g, const SbState& s) {
     e.move_id = 0; e.x = (u8)(t & 3); e.y = (u8)(t >> 2); e.path_len = 0;
     g.board[t] = (i8)id;
     g.occ |= 1u << t;
+    if (e.fl & EF_OWNER) g.own1 |= 1u << t;
+    if (e.fl & EF_STRUCT) g.strc |= 1u << t;
   }
   const u8* x = s.ext;
   int nm = x[0];
