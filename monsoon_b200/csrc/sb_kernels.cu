@@ -263,13 +263,29 @@ SBD_NI int decide(G& g, SbState* base, const double* w, double* scores_out, bool
   u32 m[SB_MASK_WORDS];
   legal_mask(g, m);
   double fc[SB_N_FEATURES], fn[SB_N_FEATURES];
-  const int cur_err = features(g, fc);
   Best best; best.score = 0.0; best.action = -1;
-  int k = 0, last = -1;
+  int last = -1;
   bool dirty = false;
-  for (int a = 0; a < SB_N_ACTIONS; a++) {
-    if (!(m[a >> 5] >> (a & 31) & 1)) continue;
-    if ((k++ & 31) != lane) continue;
+  int n_legal = 0;
+#pragma unroll
+  for (int i = 0; i < SB_MASK_WORDS; i++) n_legal += __popc(m[i]);
+  const int cur_err = (n_legal > 1 || scores_out) ? features(g, fc) : 0;
+  // Round r gives lane l the (32 r + l)-th legal action.  The trip count is uniform over the warp, so all
+  // lanes enter game_step/features TOGETHER (the first version walked the 156 action ids per lane and
+  // reached the fork at different iterations: ncu showed 1.00 thread per instruction in every step function).
+#pragma unroll 1
+  for (int r = 0; r * 32 < n_legal; r++) {
+    int k = r * 32 + lane, a = -1;
+    if (k < n_legal) {
+#pragma unroll 1
+      for (int wd = 0; wd < SB_MASK_WORDS; wd++) {
+        int c = __popc(m[wd]);
+        if (k < c) { u32 v = m[wd]; for (int q = 0; q < k; q++) v &= v - 1; a = wd * 32 + __ffs(v) - 1; break; }
+        k -= c;
+      }
+    }
+    if (a < 0) continue;
+    if (n_legal == 1 && !scores_out) { best.score = 0.0; best.action = a; break; }  // forced move: argmax of one
     if (dirty) unpack(g, *base);
     game_step(g, a);
     dirty = true; last = a;
