@@ -24,6 +24,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT]
 
 B_STEP = 2 * 512 + 1 + 20 + 2  # algorithmic bytes per env step: state in+out, action, mask, reward/done
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_rollout_random launch at the named workload, from the
+# ncu --set full capture profiles/r1_prof_bench_rollout_r1_raw.csv (9.29 MB + 1.31 MB)
+NCU_TRAFFIC_BYTES_PER_LAUNCH_4096 = 10_600_448
 METRIC = "env_steps_per_sec"
 WORKLOAD = "4096 parallel games/GPU, uniform-random legal agents, default decks, played to completion (max 400 steps)"
 
@@ -265,7 +268,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": "env_steps/s", "h2d_bytes_per_step": n * 8 + 24 + 2,
                     "d2h_bytes_per_step": n * 512 + n * 4},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_rollout_random", "peak_source": peak_src,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH_4096 if n == 4096 else None,
+                         "traffic_unit": "bytes per launch (ncu, profiles/r1_summary.md)", "kernel": "k_rollout_random", "peak_source": peak_src,
                          "algorithmic_bytes_per_env_step": B_STEP},
             "clocks": sampler.summary(),
         }
