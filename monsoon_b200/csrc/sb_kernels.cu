@@ -162,10 +162,13 @@ SBD_FI int pick_action(const G& g) {
   }
   return SB_ACTION_PASS;
 }
-template <bool DIGEST>
-__global__ void __launch_bounds__(TPB_GAME) k_rollout_random(int n, u8* states, int max_steps, int* steps_out,
-                                                             unsigned long long* chain, const DCard* cards, const double* wt,
-                                                             int gpw, int turn_sync) {
+// TPB / BSYNC: with BSYNC the two phases are separated by CTA-wide votes (__syncthreads_or) instead of
+// warp votes, so all TPB/32 warps of a CTA walk the PASS pipeline at the same time and share the
+// instruction-cache lines they fetch (the saturated kernel is instruction-fetch bound).
+template <bool DIGEST, int TPB, bool BSYNC>
+__global__ void __launch_bounds__(TPB) k_rollout_random(int n, u8* states, int max_steps, int* steps_out,
+                                                        unsigned long long* chain, const DCard* cards, const double* wt,
+                                                        int gpw, int turn_sync) {
   __shared__ DCard s_cards[SBC_COUNT];
   stage_cards(s_cards, cards);
   // gpw games per warp on CONSECUTIVE lanes (32 = plain thread per game).  Fewer games per warp = fewer
@@ -199,14 +202,14 @@ __global__ void __launch_bounds__(TPB_GAME) k_rollout_random(int n, u8* states, 
     }
   } else {
     bool at_pass = false;
-    while (__any_sync(FULL, alive)) {
+    while (BSYNC ? __syncthreads_or(alive) : __any_sync(FULL, alive)) {
       for (;;) {  // phase A: non-PASS actions
         int a = -1;
         if (alive && !at_pass) {
           a = pick_action(g);
           if (a == SB_ACTION_PASS) { at_pass = true; a = -1; }
         }
-        if (!__any_sync(FULL, a >= 0)) break;
+        if (!(BSYNC ? __syncthreads_or(a >= 0) : __any_sync(FULL, a >= 0))) break;
         if (a >= 0) {
           game_step(g, a);
           end_of_step(g);
@@ -396,6 +399,7 @@ struct SbHandle {
   int gpw;  // games per warp for the thread-per-game shape (0 = choose by batch size)
   int persistent;  // retired (measured: no gain over the hardware CTA scheduler)
   int turn_sync;   // 1: turn-synchronous warp schedule in the rollout kernel
+  int block_sync;  // 0, or 128/256/512: CTA size whose warps change phase together (CTA-wide votes)
   int ctas_per_sm;
   unsigned int* d_counter;
 };
@@ -418,9 +422,20 @@ static void launch_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max
     const int per_warp = (n + h->sm_count * 2 - 1) / (h->sm_count * 2);
     gpw = per_warp >= 24 ? 32 : per_warp >= 12 ? 16 : 8;
   }
-  k_rollout_random<DIGEST><<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, st>>>(n, states_d, max_steps, steps_d,
-                                                                                  (unsigned long long*)chain_d, h->d_cards, h->d_wt, gpw,
-                                                                                  h->turn_sync);
+  unsigned long long* ch = (unsigned long long*)chain_d;
+  int bs = h->block_sync;
+  if (bs < 0) bs = n >= 196608 ? 1024 : n >= 49152 ? 512 : 0;  // auto (tools/sweep_bsync.py): pays off once the chip is full
+  if (bs >= 1024 && h->turn_sync)
+    k_rollout_random<DIGEST, 1024, true><<<grid_for(n, gpw * 32), 1024, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1);
+  else if (bs >= 512 && h->turn_sync)
+    k_rollout_random<DIGEST, 512, true><<<grid_for(n, gpw * 16), 512, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1);
+  else if (bs >= 256 && h->turn_sync)
+    k_rollout_random<DIGEST, 256, true><<<grid_for(n, gpw * 8), 256, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1);
+  else if (bs >= 128 && h->turn_sync)
+    k_rollout_random<DIGEST, 128, true><<<grid_for(n, gpw * 4), 128, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1);
+  else
+    k_rollout_random<DIGEST, TPB_GAME, false><<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, st>>>(n, states_d, max_steps, steps_d, ch,
+                                                                                                    h->d_cards, h->d_wt, gpw, h->turn_sync);
 }
 
 extern "C" {
@@ -472,20 +487,21 @@ int sb_create(int device, SbHandle** out) {
   CK(cudaMalloc(&h->d_counter, 256));
   h->persistent = 0;
   h->turn_sync = 1;
+  h->block_sync = -1;
   {
     // shared-memory carveout: left to the driver by default.  Measured (tools/sweep_sync.py): forcing
     // MaxL1 halves the saturated throughput (the 3 KB card table per CTA no longer fits 16 CTAs/SM).
     const char* co = getenv("SB_CARVEOUT");
     const int carve = co ? atoi(co) : 25;  // 25 % = 57 KB shared: fits 16 CTAs x 3 KB, leaves ~170 KB of L1 (+2-4 % measured vs driver default)
     if (carve >= 0) {
-      CK(cudaFuncSetAttribute(k_rollout_random<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-      CK(cudaFuncSetAttribute(k_rollout_random<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      CK(cudaFuncSetAttribute(k_rollout_random<false, TPB_GAME, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      CK(cudaFuncSetAttribute(k_rollout_random<true, TPB_GAME, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
       CK(cudaFuncSetAttribute(k_rollout_heuristic, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
       CK(cudaFuncSetAttribute(k_select_action, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
       CK(cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     }
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rollout_random<false>, TPB_GAME, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rollout_random<false, TPB_GAME, false>, TPB_GAME, 0));
     h->ctas_per_sm = nb > 0 ? nb : 8;
   }
   CK(cudaMalloc(&h->d_wt, sizeof wt));
@@ -566,6 +582,7 @@ int sb_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max_steps, int3
 int sb_set_option(SbHandle* h, const char* key, int value) {
   if (!strcmp(key, "lanes_per_game")) return 0;  // retired shape (measured slower); accepted and ignored
   if (!strcmp(key, "turn_sync")) { h->turn_sync = value; return 0; }
+  if (!strcmp(key, "block_sync")) { h->block_sync = value; return 0; }
   if (!strcmp(key, "games_per_warp")) { h->gpw = value; return 0; }
   if (!strcmp(key, "persistent")) { h->persistent = value; return 0; }
   if (!strcmp(key, "ctas_per_sm")) { h->ctas_per_sm = value; return 0; }

@@ -175,6 +175,19 @@ def game_seed(base_seed, generation, i, j, k):
     return (x * 0x2545F4914F6CDD1D) & 0x7FFFFFFFFFFFFFFF
 
 
+def game_seed_array(base_seed, generation, i, j, k):
+    """Vectorised game_seed (uint64 wrap-around arithmetic == the & 0x7FFF... masks of the scalar version)."""
+    M = np.uint64(0x7FFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        x = (np.uint64(int(base_seed) & 0xFFFFFFFFFFFFFFFF) * np.uint64(0x9E3779B97F4A7C15)
+             + np.uint64(generation) * np.uint64(0xBF58476D1CE4E5B9)
+             + i.astype(np.uint64) * np.uint64(0x94D049BB133111EB)
+             + j.astype(np.uint64) * np.uint64(0xD6E8FEB86659FD93) + k.astype(np.uint64)) & M
+        x ^= x >> np.uint64(31)
+        x = (x * np.uint64(0x2545F4914F6CDD1D)) & M
+    return x.astype(np.int64)
+
+
 class FitnessEvaluator:
     """evo/fitness.py:18-259.  evaluate_population(population, generation) -> List[float] in [0, 1].
 
@@ -243,6 +256,21 @@ class FitnessEvaluator:
         self._update_hall_of_fame(population, fitness)
         return fitness
 
+    def evaluate_vs(self, population, opponents, generation=0, games_per_opponent=None):
+        """Added schedule: every individual plays `games_per_opponent` games as FIRST
+        against each fixed opponent (a baseline vector, hall of fame ...).  Same kernels, same reduction;
+        returns (wins + 0.5 draws) / games per individual."""
+        n = len(population)
+        g = int(games_per_opponent or self.config.games_per_pairing)
+        pairs = [(i, n + b) for i in range(n) for b in range(len(opponents))]
+        start = time.time()
+        counts = self._play(population, list(population) + list(opponents), pairs, g, generation)
+        self.last_counts = counts
+        self.total_games += len(pairs) * g
+        self.total_time += time.time() - start
+        per = len(opponents) * g
+        return [float(c[0] + 0.5 * c[1]) / per for c in counts]
+
     def _play(self, population, all_opponents, pairs, g, generation):
         import torch.distributed as dist
         eng = self._engine()
@@ -263,8 +291,7 @@ class FitnessEvaluator:
             gi = np.arange(c0, c1, dtype=np.int64)
             pi, k = gi // g, gi % g
             i_idx, j_idx = pair_arr[pi, 0], pair_arr[pi, 1]
-            seeds = np.array([game_seed(base_seed, generation, int(a), int(b), int(c)) for a, b, c in zip(i_idx, j_idx, k)],
-                             dtype=np.int64)
+            seeds = game_seed_array(base_seed, generation, i_idx, j_idx, k)
             idx_first = torch.as_tensor(i_idx.astype(np.int32)).to(dev)
             idx_second = torch.as_tensor(j_idx.astype(np.int32)).to(dev)
             states = eng.reset(torch.as_tensor(seeds).to(dev))
