@@ -333,38 +333,50 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select_action(int n, con
   if (lane == 0) actions[gi] = (u8)a;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_rollout_heuristic(int n, u8* states, const double* w_first, const double* w_second,
-                                                                          const int* idx_first, const int* idx_second, int max_steps,
-                                                                          i8* result, int* steps_out, const DCard* cards, const double* wt) {
+// WPC warps (games) per CTA.  BSYNC: all warps of the CTA take their decisions in step (CTA-wide vote per
+// decision), so they walk fork/step/features at the same time and share instruction-cache lines.
+template <int WPC, bool BSYNC>
+__global__ void __launch_bounds__(WPC * 32) k_rollout_heuristic(int n, u8* states, const double* w_first, const double* w_second,
+                                                                const int* idx_first, const int* idx_second, int max_steps,
+                                                                i8* result, int* steps_out, const DCard* cards, const double* wt) {
   __shared__ DCard s_cards[SBC_COUNT];
-  __shared__ __align__(16) SbState s_base[WARPS_PER_CTA];
+  __shared__ __align__(16) SbState s_base[WPC];
   stage_cards(s_cards, cards);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gi = blockIdx.x * WARPS_PER_CTA + warp;
-  if (gi >= n) return;
+  const int gi = blockIdx.x * WPC + warp;
+  const bool has_game = gi < n;
+  if (!BSYNC && !has_game) return;
   SbState* base = &s_base[warp];
-  reinterpret_cast<uint4*>(base)[lane] = reinterpret_cast<const uint4*>(states + (size_t)gi * SB_STATE_BYTES)[lane];
-  __syncwarp();
   G g;
   init_g(g, s_cards, wt);
   double wf[SB_N_FEATURES], ws[SB_N_FEATURES];
-  const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
-  const double* ps = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
-  for (int k = 0; k < SB_N_FEATURES; k++) { wf[k] = pf[k]; ws[k] = ps[k]; }
-  int k = 0, res = -1;
-  while (k < max_steps) {
-    if (base->pl[0].base < 0 || base->pl[1].base < 0) break;
-    decide(g, base, base->player_sign == 1 ? wf : ws, nullptr, true);
-    k++;
-    if (base->err) { res = -2; break; }
-  }
-  if (res != -2) {
-    bool l0 = base->pl[0].base < 0, l1 = base->pl[1].base < 0;
-    res = (l1 && !l0) ? 0 : (l0 && !l1) ? 1 : -1;
+  if (has_game) {
+    reinterpret_cast<uint4*>(base)[lane] = reinterpret_cast<const uint4*>(states + (size_t)gi * SB_STATE_BYTES)[lane];
+    const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
+    const double* ps = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
+    for (int k = 0; k < SB_N_FEATURES; k++) { wf[k] = pf[k]; ws[k] = ps[k]; }
   }
   __syncwarp();
-  reinterpret_cast<uint4*>(states + (size_t)gi * SB_STATE_BYTES)[lane] = reinterpret_cast<const uint4*>(base)[lane];
-  if (lane == 0) { if (result) result[gi] = (i8)res; if (steps_out) steps_out[gi] = k; }
+  int k = 0, res = -1;
+  bool alive = has_game;
+  for (;;) {
+    if (alive && (k >= max_steps || base->pl[0].base < 0 || base->pl[1].base < 0)) alive = false;
+    if (BSYNC) { if (!__syncthreads_or(alive)) break; } else if (!alive) break;
+    if (alive) {
+      decide(g, base, base->player_sign == 1 ? wf : ws, nullptr, true);
+      k++;
+      if (base->err) { res = -2; alive = false; }
+    }
+  }
+  if (has_game) {
+    if (res != -2) {
+      bool l0 = base->pl[0].base < 0, l1 = base->pl[1].base < 0;
+      res = (l1 && !l0) ? 0 : (l0 && !l1) ? 1 : -1;
+    }
+    __syncwarp();
+    reinterpret_cast<uint4*>(states + (size_t)gi * SB_STATE_BYTES)[lane] = reinterpret_cast<const uint4*>(base)[lane];
+    if (lane == 0) { if (result) result[gi] = (i8)res; if (steps_out) steps_out[gi] = k; }
+  }
 }
 
 __global__ void k_accumulate_fitness(int n, const i8* result, const int* idx_first, int* counts) {
@@ -395,13 +407,11 @@ struct SbHandle {
   // staging for the *_host entry points
   u8* d_stage; size_t stage_bytes;
   cudaStream_t stream;
-  int lpg;  // lanes per game for the rollout kernels (0 or 1 = thread per game)
   int gpw;  // games per warp for the thread-per-game shape (0 = choose by batch size)
-  int persistent;  // retired (measured: no gain over the hardware CTA scheduler)
   int turn_sync;   // 1: turn-synchronous warp schedule in the rollout kernel
   int block_sync;  // 0, or 128/256/512: CTA size whose warps change phase together (CTA-wide votes)
+  int heur_wpc;    // heuristic rollout: 4 (independent warps) or 8/16/32 warps per CTA deciding in step
   int ctas_per_sm;
-  unsigned int* d_counter;
 };
 
 static int fail(SbHandle* h, cudaError_t e, const char* what) {
@@ -417,10 +427,10 @@ static void launch_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max
                                   cudaStream_t st) {
   int gpw = h->gpw;
   if (gpw <= 0 || gpw > 32) {
-    // auto (measured, tools/sweep_sync.py): full warps as soon as there are ~2 warps of games per SM; below
-    // that, halve the games per warp so that every SM still gets a warp (4096 games -> 16 per warp)
-    const int per_warp = (n + h->sm_count * 2 - 1) / (h->sm_count * 2);
-    gpw = per_warp >= 24 ? 32 : per_warp >= 12 ? 16 : 8;
+    // auto (measured, tools/sweep_gpw.py): aim at ~3.5 warps per SM while the batch is small
+    // (4096 games -> 8 per warp, 8192 -> 16, 16384 and up -> full warps)
+    const int per_warp = (2 * n + h->sm_count * 7 - 1) / (h->sm_count * 7);
+    gpw = per_warp > 16 ? 32 : per_warp > 8 ? 16 : 8;
   }
   unsigned long long* ch = (unsigned long long*)chain_d;
   int bs = h->block_sync;
@@ -484,10 +494,9 @@ int sb_create(int device, SbHandle** out) {
   static double wt[WT_N];
   volatile double w = 1.0;  // player.py:32,59: w*1.6+100 with two roundings (volatile blocks FMA contraction)
   for (int i = 0; i < WT_N; i++) { wt[i] = w; volatile double m = w * 1.6; w = m + 100.0; }
-  CK(cudaMalloc(&h->d_counter, 256));
-  h->persistent = 0;
   h->turn_sync = 1;
   h->block_sync = -1;
+  h->heur_wpc = -1;
   {
     // shared-memory carveout: left to the driver by default.  Measured (tools/sweep_sync.py): forcing
     // MaxL1 halves the saturated throughput (the 3 KB card table per CTA no longer fits 16 CTAs/SM).
@@ -496,7 +505,6 @@ int sb_create(int device, SbHandle** out) {
     if (carve >= 0) {
       CK(cudaFuncSetAttribute(k_rollout_random<false, TPB_GAME, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
       CK(cudaFuncSetAttribute(k_rollout_random<true, TPB_GAME, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-      CK(cudaFuncSetAttribute(k_rollout_heuristic, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
       CK(cudaFuncSetAttribute(k_select_action, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
       CK(cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     }
@@ -507,9 +515,7 @@ int sb_create(int device, SbHandle** out) {
   CK(cudaMalloc(&h->d_wt, sizeof wt));
   CK(cudaMemcpy(h->d_wt, wt, sizeof wt, cudaMemcpyHostToDevice));
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  const char* env = getenv("SB_LPG");
-  h->lpg = env ? atoi(env) : 0;
-  env = getenv("SB_GPW");
+  const char* env = getenv("SB_GPW");
   h->gpw = env ? atoi(env) : 0;
   return 0;
 }
@@ -518,7 +524,6 @@ int sb_destroy(SbHandle* h) {
   cudaSetDevice(h->device);
   if (h->d_cards) cudaFree(h->d_cards);
   if (h->d_wt) cudaFree(h->d_wt);
-  if (h->d_counter) cudaFree(h->d_counter);
   if (h->d_stage) cudaFree(h->d_stage);
   if (h->stream) cudaStreamDestroy(h->stream);
   free(h);
@@ -583,8 +588,8 @@ int sb_set_option(SbHandle* h, const char* key, int value) {
   if (!strcmp(key, "lanes_per_game")) return 0;  // retired shape (measured slower); accepted and ignored
   if (!strcmp(key, "turn_sync")) { h->turn_sync = value; return 0; }
   if (!strcmp(key, "block_sync")) { h->block_sync = value; return 0; }
+  if (!strcmp(key, "heur_wpc")) { h->heur_wpc = value; return 0; }
   if (!strcmp(key, "games_per_warp")) { h->gpw = value; return 0; }
-  if (!strcmp(key, "persistent")) { h->persistent = value; return 0; }
   if (!strcmp(key, "ctas_per_sm")) { h->ctas_per_sm = value; return 0; }
   return -1;
 }
@@ -592,8 +597,13 @@ int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_
                          const int32_t* idx_first_d, const int32_t* idx_second_d, int max_steps, int8_t* result_d, int32_t* steps_d,
                          void* stream) {
   if (n <= 0) return 0;
-  k_rollout_heuristic<<<grid_for(n, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-      n, states_d, w_first_d, w_second_d, idx_first_d, idx_second_d, max_steps, (i8*)result_d, steps_d, h->d_cards, h->d_wt);
+  cudaStream_t st = (cudaStream_t)stream;
+  int hw = h->heur_wpc;
+  if (hw < 0) hw = n >= 49152 ? 32 : 4;  // auto (tools/sweep_heur.py)
+#define HEUR(W, B) k_rollout_heuristic<W, B><<<grid_for(n, W), W * 32, 0, st>>>(n, states_d, w_first_d, w_second_d, idx_first_d, idx_second_d, \
+                                                                             max_steps, (i8*)result_d, steps_d, h->d_cards, h->d_wt)
+  if (hw >= 32) HEUR(32, true); else if (hw >= 16) HEUR(16, true); else if (hw >= 8) HEUR(8, true); else HEUR(4, false);
+#undef HEUR
   LAUNCH_CHECK();
   return 0;
 }

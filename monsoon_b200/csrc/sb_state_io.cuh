@@ -4,8 +4,6 @@
 #pragma once
 #include "sb_engine.cuh"
 
-SBD_FI u32 fnv_step(u32 dummy) { return dummy; }
-
 // 128-bit vectorised copy of one packed state (global or shared <-> local)
 SBD_FI void load_state(SbState& dst, const void* src) {
   const uint4* s = reinterpret_cast<const uint4*>(src);
