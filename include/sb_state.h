@@ -95,8 +95,9 @@ typedef struct SbState {
   uint8_t pad[3];
   SbPlayer pl[2];
   SbTile tile[SB_N_TILES];
-  /* ext[0] = n B005 memories, ext[1..90] = 9 x {temple tile, pos, card, tile flags, strength i16, status u32}
-   * (cards/b005.py:13,24-33); ext[91] = n board-instance card records, ext[92..107] = 4 x {order<<7 |
+  /* ext[0] = n B005 memories, ext[1..90] = 9 x {key, pos, card, tile flags, strength i16, status u32}
+   * (cards/b005.py:13,24-33); key = tile of the owning temple, or 0x80 | index of the remembered temple COPY
+   * (an earlier record) whose own memory this is -- deep copies keep their lists; pre-order, temples by tile; ext[91] = n board-instance card records, ext[92..107] = 4 x {order<<7 |
    * in_deck<<6 | index, tile or 0xFF, frozen strength i16} (cards/b305.py:41-45). */
   uint8_t ext[SB_EXT_BYTES];
 } SbState;

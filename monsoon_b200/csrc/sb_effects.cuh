@@ -62,6 +62,56 @@ SBD_NI int frontmost(G& g, const Target& t, i8* pts) {
   return n;
 }
 
+// ---- Temple of Time memories (cards/b005.py:13,24-33): a forest of deep copies, see Mem in sb_engine.cuh
+SBD_NI int mem_push_entity(G& g, int temple, int parent, int pos, const Ent& s) {
+  if (g.n_mem >= NMEM) { GERR(g, SB_ERR_OVERFLOW); return -1; }
+  Mem& m = g.mem[g.n_mem];
+  m.b005 = (i8)temple; m.parent = (i8)parent; m.pos = (u8)pos; m.card = s.card; m.fl = s.fl & (EF_OWNER | EF_STRUCT | EF_FIXED);
+  m.strength = s.strength;
+  #pragma unroll 1
+  for (int k = 0; k < 5; k++) m.st[k] = s.st[k];
+  return g.n_mem++;
+}
+// deep copy of the subtree rooted at mem[src] under new_parent (iterative: parents precede children in the array)
+SBD_NI int mem_copy_subtree(G& g, int src, int new_parent, int limit) {
+  i8 map[NMEM];
+  #pragma unroll 1
+  for (int q = 0; q < NMEM; q++) map[q] = -1;
+  int root = -1;
+  #pragma unroll 1
+  for (int q = src; q < limit; q++) {
+    const int par = g.mem[q].parent;
+    const bool is_root = (q == src);
+    if (!is_root && (par < 0 || map[par] < 0)) continue;
+    if (g.n_mem >= NMEM) { GERR(g, SB_ERR_OVERFLOW); return -1; }
+    const int me = g.n_mem++;
+    g.mem[me] = g.mem[q];
+    g.mem[me].b005 = -1;
+    g.mem[me].fl |= EF_SINGLE;  // detached: deep-copied below another temple's copy (lives on a cloned board once restored)
+    g.mem[me].parent = (i8)(is_root ? new_parent : map[par]);
+    map[q] = (i8)me;
+    if (is_root) root = me;
+  }
+  return root;
+}
+SBD_NI void mem_delete_temple(G& g, int temple) {  // self.ability_remembered = []
+  u8 keep[NMEM], nidx[NMEM];
+  int w = 0;
+  #pragma unroll 1
+  for (int i = 0; i < g.n_mem; i++) {
+    const Mem& m = g.mem[i];
+    bool k = m.parent < 0 ? (m.b005 != temple) : (keep[m.parent] != 0);
+    keep[i] = k; nidx[i] = k ? (u8)w++ : (u8)0xFF;
+  }
+  #pragma unroll 1
+  for (int i = 0; i < g.n_mem; i++) if (keep[i]) {
+    Mem m = g.mem[i];
+    if (m.parent >= 0) m.parent = (i8)nidx[m.parent];
+    g.mem[nidx[i]] = m;
+  }
+  g.n_mem = (u8)w;
+}
+
 SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
   Ent& e = g.e[id];
   const DCard& cd = CARD(g, e.card);
@@ -84,46 +134,48 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
       for (int i = 0; i < n; i++) { deal_damage_pt(g, pts[i], p[0], 1); if (g.err) return; }
       destroy(g, id, 1);
       break;
-    case SBC_B005: {  // cards/b005.py:15-33 (a remembered B005 copy loses its own memory: documented deviation)
+    case SBC_B005: {  // cards/b005.py:15-33, including the memories of remembered temple copies (deepcopy)
       t = mkT(TK_ANY, TS_FRIENDLY);
       n = surrounding(g, ex, ey, CUR(g), &t, pts);
       int mine = 0;
       #pragma unroll 1
-      for (int i = 0; i < g.n_mem; i++) if (g.mem[i].b005 == id) mine++;
+      for (int i = 0; i < g.n_mem; i++) if (g.mem[i].parent < 0 && g.mem[i].b005 == id) mine++;
       if (mine == 0) {
         #pragma unroll 1
         for (int i = 0; i < n; i++) {
           tid = need(g, pts[i]);
           if (tid < 0) return;
-          if (g.n_mem >= NMEM) { GERR(g, SB_ERR_OVERFLOW); return; }
-          Mem& m = g.mem[g.n_mem++];
-          const Ent& s = g.e[tid];
-          m.b005 = (i8)id; m.pos = (u8)pts[i]; m.card = s.card; m.fl = s.fl & (EF_OWNER | EF_STRUCT | EF_FIXED); m.strength = s.strength;
-          if (s.card == SBC_B005) for (int q = 0; q < g.n_mem - 1; q++) if (g.mem[q].b005 == tid) m.fl |= EF_SINGLE;  // EF_SINGLE bit doubles as "nested memories" here
-          #pragma unroll 1
-          for (int k = 0; k < 5; k++) m.st[k] = s.st[k];
+          int r = mem_push_entity(g, id, -1, pts[i], g.e[tid]);
+          if (r < 0) return;
+          if (g.e[tid].card == SBC_B005) {  // the copy carries a deep copy of that temple's own memories
+            const int nm0 = g.n_mem;
+            #pragma unroll 1
+            for (int q = 0; q < nm0; q++)
+              if (g.mem[q].parent < 0 && g.mem[q].b005 == tid && mem_copy_subtree(g, q, r, nm0) < 0) return;
+          }
         }
       } else {
         int count = 0;
+        const int nm0 = g.n_mem;
         #pragma unroll 1
-        for (int i = 0; i < g.n_mem && count < p[0]; i++) {
+        for (int i = 0; i < nm0 && count < p[0]; i++) {
           const Mem m = g.mem[i];
-          if (m.b005 != id) continue;
+          if (m.parent >= 0 || m.b005 != id) continue;
           int occ = at_pt(g, m.pos);
           if (occ < 0 || (g.e[occ].card == m.card && ((g.e[occ].fl ^ m.fl) & (EF_OWNER | EF_STRUCT)) == 0)) {
-            if (m.fl & EF_SINGLE) { GERR(g, SB_ERR_UNSUPPORTED); return; }  // memories of a remembered temple are not modelled
+            if (m.fl & EF_SINGLE) { GERR(g, SB_ERR_UNSUPPORTED); return; }  // detached copy: not modelled
             int c = new_ent(g, m.card, m.fl & EF_OWNER, m.strength);
             g.e[c].fl = (u8)((g.e[c].fl & ~EF_FIXED) | (m.fl & EF_FIXED));
             #pragma unroll 1
             for (int k = 0; k < 5; k++) g.e[c].st[k] = m.st[k];
             set_xy(g, PTX(m.pos), PTY(m.pos), c);
+            #pragma unroll 1
+            for (int q = i + 1; q < nm0; q++)  // the restored object keeps its own ability_remembered
+              if (g.mem[q].parent == i) { g.mem[q].parent = -1; g.mem[q].b005 = (i8)c; }
             count++;
           }
         }
-        int w = 0;
-        #pragma unroll 1
-        for (int i = 0; i < g.n_mem; i++) if (g.mem[i].b005 != id) g.mem[w++] = g.mem[i];
-        g.n_mem = (u8)w;
+        mem_delete_temple(g, id);
       }
       break; }
     case SBC_B006: {  // cards/b006.py:14-39: ability_strength, ability_targets

@@ -83,7 +83,9 @@ struct Ply {  // player.py:13-37
   CardRec hand[HAND_W];  // working capacity > packed capacity: a cycle holds 17 deck cards for a moment
   CardRec deck[DECK_W];
 };
-struct Mem { i8 b005; u8 pos, card, fl; i16 strength; u8 st[5]; u8 pad; };  // cards/b005.py remembered copies
+// cards/b005.py remembered deep copies.  parent < 0: a memory of the live temple entity `b005`; parent >= 0: a
+// memory held BY the remembered temple copy mem[parent] (its own ability_remembered); parent index < own index.
+struct Mem { i8 b005; u8 pos, card, fl; i16 strength; u8 st[5]; i8 parent; };
 
 struct G {
   Ent e[MAXE];
@@ -910,12 +912,20 @@ SBD_NI void compact(G& g) {
     }
   }
   int w = 0;
-  #pragma unroll 1
-  for (int i = 0; i < g.n_mem; i++) {
-    if (g.mem[i].b005 < 0) continue;
-    u8 r = remap[g.mem[i].b005];
-    if (r == 0xFF) continue;
-    g.mem[w] = g.mem[i]; g.mem[w].b005 = (i8)r; w++;
+  {  // a memory survives iff the temple at the root of its tree is still on the board
+    u8 keep[NMEM], nidx[NMEM];
+    #pragma unroll 1
+    for (int i = 0; i < g.n_mem; i++) {
+      const Mem& m = g.mem[i];
+      bool k = m.parent < 0 ? (m.b005 >= 0 && remap[m.b005] != 0xFF) : (keep[m.parent] != 0);
+      keep[i] = k; nidx[i] = k ? (u8)w++ : (u8)0xFF;
+    }
+    #pragma unroll 1
+    for (int i = 0; i < g.n_mem; i++) if (keep[i]) {
+      Mem m = g.mem[i];
+      if (m.parent >= 0) m.parent = (i8)nidx[m.parent]; else m.b005 = (i8)remap[m.b005];
+      g.mem[nidx[i]] = m;
+    }
   }
   g.n_mem = (u8)w;
   // what would not fit the packed layout is an overflow there too (keeps rollouts == step-per-launch)

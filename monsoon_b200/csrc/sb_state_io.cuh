@@ -68,9 +68,11 @@ SBD_NI void unpack(G& g, const SbState& s) {
   for (int i = 0; i < nm && i < NMEM_PACKED; i++) {
     const u8* r = x + 1 + 10 * i;
     Mem& m = g.mem[g.n_mem++];
-    m.b005 = (i8)at_pt(g, r[0]);
+    if (r[0] & 0x80) { m.parent = (i8)(r[0] & 0x7F); m.b005 = -1; }  // memory of the remembered temple copy #parent
+    else { m.parent = -1; m.b005 = (i8)at_pt(g, r[0]); }
     m.pos = r[1]; m.card = r[2];
-    m.fl = (u8)(((r[3] & SB_TF_OWNER) ? EF_OWNER : 0) | ((r[3] & SB_TF_STRUCTURE) ? EF_STRUCT : 0) | ((r[3] & SB_TF_FIXED) ? EF_FIXED : 0) | ((r[3] & 8) ? EF_SINGLE : 0));
+    m.fl = (u8)(((r[3] & SB_TF_OWNER) ? EF_OWNER : 0) | ((r[3] & SB_TF_STRUCTURE) ? EF_STRUCT : 0) | ((r[3] & SB_TF_FIXED) ? EF_FIXED : 0) |
+                ((r[3] & 8) ? EF_SINGLE : 0));  // bit 3 = detached copy
     m.strength = (i16)(r[4] | (r[5] << 8));
     u32 w = r[6] | (r[7] << 8) | (r[8] << 16) | ((u32)r[9] << 24);
 #pragma unroll
@@ -90,6 +92,36 @@ SBD_NI void unpack(G& g, const SbState& s) {
   }
 }
 
+// one memory tree in pre-order (explicit stack; key = owning temple tile, or 0x80 | packed index of the parent copy)
+SBD_NI void pack_mem(const G& g, SbState& s, int root, int root_key, int& nm) {
+  i8 st_idx[NMEM];
+  u8 st_key[NMEM];
+  int sp = 0;
+  st_idx[sp] = (i8)root; st_key[sp] = (u8)root_key; sp++;
+  #pragma unroll 1
+  while (sp > 0) {
+    sp--;
+    const int i = st_idx[sp];
+    const int key = st_key[sp];
+    if (nm >= NMEM_PACKED) { if (!s.err) s.err = SB_ERR_OVERFLOW; return; }
+    const Mem& m = g.mem[i];
+    const int me = nm++;
+    u8* r = s.ext + 1 + 10 * me;
+    r[0] = (u8)key; r[1] = m.pos; r[2] = m.card;
+    r[3] = (u8)(((m.fl & EF_OWNER) ? SB_TF_OWNER : 0) | ((m.fl & EF_STRUCT) ? SB_TF_STRUCTURE : 0) | ((m.fl & EF_FIXED) ? SB_TF_FIXED : 0) |
+               ((m.fl & EF_SINGLE) ? 8 : 0));
+    r[4] = (u8)(m.strength & 255); r[5] = (u8)((m.strength >> 8) & 255);
+    u32 w = 0;
+    if (!(m.fl & EF_STRUCT)) {
+      #pragma unroll 1
+      for (int k = 0; k < 5; k++) w |= (u32)(m.st[k] > 63 ? 63 : m.st[k]) << (SB_ST_BITS * k);
+    }
+    r[6] = (u8)(w & 255); r[7] = (u8)((w >> 8) & 255); r[8] = (u8)((w >> 16) & 255); r[9] = (u8)((w >> 24) & 255);
+    #pragma unroll 1
+    for (int q = g.n_mem - 1; q > i; q--)  // children pushed in reverse so the lowest index pops first
+      if (g.mem[q].parent == i && sp < NMEM) { st_idx[sp] = (i8)q; st_key[sp] = (u8)(0x80 | me); sp++; }
+  }
+}
 SBD_NI void pack(const G& g, SbState& s) {
   uint4* z = reinterpret_cast<uint4*>(&s);
 #pragma unroll 8
@@ -135,22 +167,12 @@ SBD_NI void pack(const G& g, SbState& s) {
   u8* x = s.ext;
   int nm = 0;
   #pragma unroll 1
-  for (int tile = 0; tile < SB_N_TILES; tile++) {  // canonical order: temples in tile order, copies in memory order
+  for (int tile = 0; tile < SB_N_TILES; tile++) {  // canonical order: temples in tile order, each memory followed by its subtree
     int bid = g.board[tile];
     if (bid < 0 || g.e[bid].card != SBC_B005) continue;
     #pragma unroll 1
-    for (int i = 0; i < g.n_mem; i++) {
-      const Mem& m = g.mem[i];
-      if (m.b005 != bid) continue;
-      if (nm >= NMEM_PACKED) { if (!s.err) s.err = SB_ERR_OVERFLOW; break; }
-      u8* r = x + 1 + 10 * nm++;
-      r[0] = (u8)tile; r[1] = m.pos; r[2] = m.card;
-      r[3] = (u8)(((m.fl & EF_OWNER) ? SB_TF_OWNER : 0) | ((m.fl & EF_STRUCT) ? SB_TF_STRUCTURE : 0) | ((m.fl & EF_FIXED) ? SB_TF_FIXED : 0) | ((m.fl & EF_SINGLE) ? 8 : 0));
-      r[4] = (u8)(m.strength & 255); r[5] = (u8)((m.strength >> 8) & 255);
-      u32 w = 0;
-      if (!(m.fl & EF_STRUCT)) for (int k = 0; k < 5; k++) w |= (u32)(m.st[k] > 63 ? 63 : m.st[k]) << (SB_ST_BITS * k);
-      r[6] = (u8)(w & 255); r[7] = (u8)((w >> 8) & 255); r[8] = (u8)((w >> 16) & 255); r[9] = (u8)((w >> 24) & 255);
-    }
+    for (int i = 0; i < g.n_mem; i++)
+      if (g.mem[i].parent < 0 && g.mem[i].b005 == bid) pack_mem(g, s, i, tile, nm);
   }
   x[0] = (u8)nm;
   int no = 0;

@@ -273,29 +273,37 @@ def pack_reference(game, steps=0, done=0, err=0):
         ext[93 + 4 * k] = tile
         ext[94 + 4 * k] = strength & 255
         ext[95 + 4 * k] = (strength >> 8) & 255
-    nmem = 0
+    nmem = [0]
+
+    def emit_mem(m, key):
+        if nmem[0] >= 9:
+            raise PackOverflow()
+        me = nmem[0]
+        nmem[0] += 1
+        is_struct = isinstance(m, r.structure.Structure)
+        base = 1 + 10 * me
+        ext[base] = key
+        ext[base + 1] = m.position.y * 4 + m.position.x
+        ext[base + 2] = card_index(m)
+        ext[base + 3] = (TF_OWNER if int(m.player.order) else 0) | (TF_STRUCTURE if is_struct else 0) | \
+                        (TF_FIXED if getattr(m, "fixedly_forward", False) else 0) | \
+                        (0 if (m.player is b.local or m.player is b.remote) else 8)  # detached: deep-copied Player/Board
+        ext[base + 4] = m.strength & 255
+        ext[base + 5] = (m.strength >> 8) & 255
+        w = 0 if is_struct else _status_word(m)
+        for q in range(4):
+            ext[base + 6 + q] = (w >> (8 * q)) & 255
+        for c in getattr(m, "ability_remembered", None) or []:  # a remembered temple copy keeps its own memories
+            emit_mem(c, 0x80 | me)
+
     for y in range(5):
         for x in range(4):
             e = b.board[y][x]
             if e is None or type(e).__name__ != "B005":
                 continue
             for m in e.ability_remembered:
-                if nmem >= 9:
-                    break
-                is_struct = isinstance(m, r.structure.Structure)
-                base = 1 + 10 * nmem
-                ext[base] = y * 4 + x
-                ext[base + 1] = m.position.y * 4 + m.position.x
-                ext[base + 2] = card_index(m)
-                ext[base + 3] = (TF_OWNER if int(m.player.order) else 0) | (TF_STRUCTURE if is_struct else 0) | \
-                                (TF_FIXED if getattr(m, "fixedly_forward", False) else 0) | \
-                                (8 if getattr(m, "ability_remembered", None) else 0)
-                ext[base + 4] = m.strength & 255
-                ext[base + 5] = (m.strength >> 8) & 255
-                w = 0 if is_struct else _status_word(m)
-                for q in range(4):
-                    ext[base + 6 + q] = (w >> (8 * q)) & 255
-                nmem += 1
+                emit_mem(m, y * 4 + x)
+    nmem = nmem[0]
     ext[0] = nmem
     for y in range(5):
         for x in range(4):

@@ -757,9 +757,11 @@ void o_unpack(Game *g, const SbState *s) {
   for (int i = 0; i < nm && i < NMEM_PACKED; i++) {
     const uint8_t *r = x + 1 + 10 * i;
     Mem *m = &g->mem[g->n_mem++];
-    m->b005 = o_at_pt(g, r[0]);
+    if (r[0] & 0x80) { m->parent = r[0] & 0x7F; m->b005 = -1; }   /* memory of the remembered temple copy #parent */
+    else { m->parent = -1; m->b005 = o_at_pt(g, r[0]); }
     m->pos = r[1]; m->card = r[2];
-    m->owner = (r[3] & SB_TF_OWNER) ? 1 : 0; m->is_struct = !!(r[3] & SB_TF_STRUCTURE); m->fixed = !!(r[3] & SB_TF_FIXED); m->nested = !!(r[3] & 8);
+    m->owner = (r[3] & SB_TF_OWNER) ? 1 : 0; m->is_struct = !!(r[3] & SB_TF_STRUCTURE); m->fixed = !!(r[3] & SB_TF_FIXED);
+    m->detached = !!(r[3] & 8);
     m->strength = (int16_t)(r[4] | (r[5] << 8));
     uint32_t w = r[6] | (r[7] << 8) | (r[8] << 16) | ((uint32_t)r[9] << 24);
     for (int k = 0; k < 5; k++) m->st[k] = (w >> (SB_ST_BITS * k)) & 63;
@@ -772,6 +774,19 @@ void o_unpack(Game *g, const SbState *s) {
     if (r[1] != 0xFF) c->link = o_at_pt(g, r[1]);
     else { c->link = -1; c->xstr = (int16_t)(r[2] | (r[3] << 8)); }
   }
+}
+static void pack_mem(const Game *g, SbState *s, int i, int key, int *nm) {
+  if (*nm >= NMEM_PACKED) { if (!s->err) s->err = SB_ERR_OVERFLOW; return; }
+  const Mem *m = &g->mem[i];
+  const int me = (*nm)++;
+  uint8_t *r = s->ext + 1 + 10 * me;
+  r[0] = (uint8_t)key; r[1] = (uint8_t)m->pos; r[2] = (uint8_t)m->card;
+  r[3] = (m->owner ? SB_TF_OWNER : 0) | (m->is_struct ? SB_TF_STRUCTURE : 0) | (m->fixed ? SB_TF_FIXED : 0) | (m->detached ? 8 : 0);
+  r[4] = (uint8_t)(m->strength & 255); r[5] = (uint8_t)((m->strength >> 8) & 255);
+  uint32_t w = 0;
+  if (!m->is_struct) for (int k = 0; k < 5; k++) w |= (uint32_t)(m->st[k] > 63 ? 63 : m->st[k]) << (SB_ST_BITS * k);
+  r[6] = w & 255; r[7] = (w >> 8) & 255; r[8] = (w >> 16) & 255; r[9] = (w >> 24) & 255;
+  for (int q = i + 1; q < g->n_mem; q++) if (g->mem[q].parent == i) pack_mem(g, s, q, 0x80 | me, nm);
 }
 void o_pack(const Game *g, SbState *s) {
   memset(s, 0, sizeof *s);
@@ -813,21 +828,11 @@ void o_pack(const Game *g, SbState *s) {
   }
   uint8_t *x = s->ext;
   int nm = 0;
-  for (int tile = 0; tile < 20; tile++) { /* canonical order: temples in tile order, each temple's copies in memory order */
+  for (int tile = 0; tile < 20; tile++) { /* canonical order: temples in tile order, each memory followed by its own subtree */
     int bid = g->board[tile >> 2][tile & 3];
     if (bid < 0 || g->e[bid].card != SBC_B005) continue;
-    for (int i = 0; i < g->n_mem; i++) {
-      const Mem *m = &g->mem[i];
-      if (m->b005 != bid) continue;
-      if (nm >= NMEM_PACKED) { s->err = s->err ? s->err : SB_ERR_OVERFLOW; break; }
-      uint8_t *r = x + 1 + 10 * nm++;
-      r[0] = (uint8_t)tile; r[1] = (uint8_t)m->pos; r[2] = (uint8_t)m->card;
-      r[3] = (m->owner ? SB_TF_OWNER : 0) | (m->is_struct ? SB_TF_STRUCTURE : 0) | (m->fixed ? SB_TF_FIXED : 0) | (m->nested ? 8 : 0);
-      r[4] = (uint8_t)(m->strength & 255); r[5] = (uint8_t)((m->strength >> 8) & 255);
-      uint32_t w = 0;
-      if (!m->is_struct) for (int k = 0; k < 5; k++) w |= (uint32_t)(m->st[k] > 63 ? 63 : m->st[k]) << (SB_ST_BITS * k);
-      r[6] = w & 255; r[7] = (w >> 8) & 255; r[8] = (w >> 16) & 255; r[9] = (w >> 24) & 255;
-    }
+    for (int i = 0; i < g->n_mem; i++)
+      if (g->mem[i].parent < 0 && g->mem[i].b005 == bid) pack_mem(g, s, i, tile, &nm);
   }
   x[0] = (uint8_t)nm;
   int no = 0;

@@ -65,7 +65,12 @@ typedef struct {  /* unit.py:8-23 / structure.py:8-16 */
  * is the object's frozen strength.  flags carries SB_CF_OBJ for them. */
 typedef struct { int card, cost, flags, wn, xstr, link; } CardRec;
 /* B005 per-instance memory (cards/b005.py:13,24-33): deep copies of neighbouring friendly entities */
-typedef struct { int b005, pos, card, owner, is_struct, fixed, nested, strength, st[5]; } Mem;  /* nested: the remembered copy was a B005 that itself had memories */
+/* parent < 0: a memory of the live temple entity `b005`; parent >= 0: a memory held BY the remembered temple
+ * copy mem[parent] (deepcopy keeps the copy's own ability_remembered list); parent index < own index always */
+typedef struct { int b005, parent, pos, card, owner, is_struct, fixed, detached, strength, st[5]; } Mem;
+/* detached: the record was deep-copied as part of ANOTHER temple's copy.  Card.copy re-points only the top
+ * object's .player (card.py:71-75); everything below keeps the deep-copied Player/Board, so such an entity
+ * would act on a cloned board once restored.  Restoring one is not modelled: SB_ERR_UNSUPPORTED. */
 #define NMEM_W 12
 #define NMEM_PACKED 9
 #define NOBJ_PACKED 4

@@ -48,6 +48,39 @@ static int count_types_friendly(Game *g) { /* cards/up02.py:13-19, up03.py:14-20
   return c;
 }
 
+/* ---- Temple of Time memories (cards/b005.py:13,24-33): a forest of deep copies, see Mem in sb_oracle.h */
+static int mem_push_entity(Game *g, int temple, int parent, int pos, const Ent *s) {
+  if (g->n_mem >= NMEM_W) { ERR(g, SB_ERR_OVERFLOW); return -1; }
+  Mem *m = &g->mem[g->n_mem];
+  m->b005 = temple; m->parent = parent; m->pos = pos; m->card = s->card; m->owner = s->owner; m->is_struct = s->is_struct;
+  m->fixed = s->fixed; m->strength = s->strength; m->detached = 0;
+  for (int k = 0; k < 5; k++) m->st[k] = s->st[k];
+  return g->n_mem++;
+}
+static int mem_copy_subtree(Game *g, int src, int new_parent, int limit) {
+  if (g->n_mem >= NMEM_W) { ERR(g, SB_ERR_OVERFLOW); return -1; }
+  int me = g->n_mem++;
+  g->mem[me] = g->mem[src];
+  g->mem[me].b005 = -1; g->mem[me].parent = new_parent; g->mem[me].detached = 1;
+  for (int q = src + 1; q < limit; q++)
+    if (g->mem[q].parent == src && mem_copy_subtree(g, q, me, limit) < 0) return -1;
+  return me;
+}
+static void mem_delete_temple(Game *g, int temple) { /* self.ability_remembered = [] */
+  int keep[NMEM_W], newidx[NMEM_W], w = 0;
+  for (int i = 0; i < g->n_mem; i++) {
+    const Mem *m = &g->mem[i];
+    keep[i] = m->parent < 0 ? (m->b005 != temple) : keep[m->parent];
+    newidx[i] = keep[i] ? w++ : -1;
+  }
+  for (int i = 0; i < g->n_mem; i++) if (keep[i]) {
+    Mem m = g->mem[i];
+    if (m.parent >= 0) m.parent = newidx[m.parent];
+    g->mem[newidx[i]] = m;
+  }
+  g->n_mem = w;
+}
+
 void o_effect(Game *g, int id, int pos_pt, int has_source) {
   Ent *e = &g->e[id];
   const int *p = OCARDS[e->card].p;
@@ -72,41 +105,41 @@ void o_effect(Game *g, int id, int pos_pt, int has_source) {
     for (int i = 0; i < n; i++) { o_deal_damage_pt(g, pts[i], p[0], 1); if (g->err) return; }
     o_destroy(g, id, 1);
     break; }
-  case SBC_B005: { /* cards/b005.py:15-33.  Deviation: a remembered B005 copy loses ITS OWN memory. */
+  case SBC_B005: { /* cards/b005.py:15-33, including the memories of remembered temple copies (deepcopy) */
     t = T(TK_ANY, TS_FRIENDLY);
     n = o_surrounding(g, e->x, e->y, CUR(g), &t, pts);
     int mine = 0;
-    for (int i = 0; i < g->n_mem; i++) if (g->mem[i].b005 == id) mine++;
+    for (int i = 0; i < g->n_mem; i++) if (g->mem[i].parent < 0 && g->mem[i].b005 == id) mine++;
     if (mine == 0) {
       for (int i = 0; i < n; i++) {
         tid = need(g, pts[i]);
         if (tid < 0) return;
-        if (g->n_mem >= NMEM_W) { ERR(g, SB_ERR_OVERFLOW); return; }
-        Mem *m = &g->mem[g->n_mem++];
-        const Ent *s = &g->e[tid];
-        m->b005 = id; m->pos = pts[i]; m->card = s->card; m->owner = s->owner; m->is_struct = s->is_struct;
-        m->fixed = s->fixed; m->strength = s->strength; m->nested = 0;
-        if (s->card == SBC_B005) for (int q = 0; q < g->n_mem; q++) if (g->mem[q].b005 == tid) m->nested = 1;
-        for (int k = 0; k < 5; k++) m->st[k] = s->st[k];
+        int r = mem_push_entity(g, id, -1, pts[i], &g->e[tid]);
+        if (r < 0) return;
+        if (g->e[tid].card == SBC_B005) { /* the copy carries a deep copy of that temple's own memories */
+          int nm0 = g->n_mem;
+          for (int q = 0; q < nm0; q++)
+            if (g->mem[q].parent < 0 && g->mem[q].b005 == tid && mem_copy_subtree(g, q, r, nm0) < 0) return;
+        }
       }
     } else {
-      int count = 0;
-      for (int i = 0; i < g->n_mem && count < p[0]; i++) {
+      int count = 0, nm0 = g->n_mem;
+      for (int i = 0; i < nm0 && count < p[0]; i++) {
         Mem *m = &g->mem[i];
-        if (m->b005 != id) continue;
+        if (m->parent >= 0 || m->b005 != id) continue;
         int occ = o_at_pt(g, m->pos);
         if (occ < 0 || (g->e[occ].is_struct == m->is_struct && g->e[occ].card == m->card && g->e[occ].owner == m->owner)) {
+          if (m->detached) { ERR(g, SB_ERR_UNSUPPORTED); return; } /* would live on a deep-copied board */
           int c = o_new_ent(g, m->card, m->owner, m->strength);
-          if (m->nested) { ERR(g, SB_ERR_UNSUPPORTED); return; } /* memories of a remembered temple are not modelled */
           g->e[c].fixed = m->fixed;
           for (int k = 0; k < 5; k++) g->e[c].st[k] = m->st[k];
           o_set(g, PTX(m->pos), PTY(m->pos), c);
+          for (int q = i + 1; q < nm0; q++) /* the restored object keeps its own ability_remembered */
+            if (g->mem[q].parent == i) { g->mem[q].parent = -1; g->mem[q].b005 = c; }
           count++;
         }
       }
-      int w = 0;
-      for (int i = 0; i < g->n_mem; i++) if (g->mem[i].b005 != id) g->mem[w++] = g->mem[i];
-      g->n_mem = w;
+      mem_delete_temple(g, id);
     }
     break; }
   case SBC_B006: { /* cards/b006.py:14-39 */
