@@ -67,6 +67,12 @@ int sb_features(SbHandle *h, int n, const uint8_t *states_d, double *feat_d, uin
 int sb_select_action(SbHandle *h, int n, const uint8_t *states_d, const double *weights_d, uint8_t *actions_d,
                      double *scores_d, void *stream);
 
+/* Stormbound.expert_action (games/stormbound.py:563-637) for n games: the scripted opponent behind
+ * Game.expert_agent (games/stormbound.py:201-209).  It draws its choices from the GAME's stream, so each
+ * state's draw counter (and err byte, for the reference's choice([]) / max([]) exceptions) is updated in
+ * place; actions_d u8[n]. */
+int sb_expert_action(SbHandle *h, int n, uint8_t *states_d, uint8_t *actions_d, void *stream);
+
 /* Uniform-random legal agent until done/err or max_steps more steps (the agent
  * stream is philox(counter=(step,0,0xA6E7,0), key=seed)).  steps_d i32[n] = steps taken by this call;
  * chain_d (nullable) u64[n] = running hash of the per-step state digests (parity evidence). */

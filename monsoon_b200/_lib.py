@@ -32,6 +32,7 @@ SIGNATURES = {
     "sb_observe": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "sb_features": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "sb_select_action": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    "sb_expert_action": (_int, [_vp, _int, _vp, _vp, _vp]),
     "sb_rollout_random": (_int, [_vp, _int, _vp, _int, _vp, _vp, _vp]),
     "sb_rollout_heuristic": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "sb_accumulate_fitness": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),

@@ -412,7 +412,9 @@ SBD_NI void spell_ability(G& g, int card, int caster, int pos_pt) {
 }
 
 // ---------------------------------------------------------------- status verbs (unit.py:239-275)
-SBD_FI void st_add(G& g, int id, int s) { if (g.e[id].st[s] < 255) g.e[id].st[s]++; }  // packed counters saturate at 63 (compact)
+SBD_FI void st_add(G& g, int id, int s) {  // 6-bit packed counters: the 64th copy of one status flags the game
+  if (g.e[id].st[s] < 63) g.e[id].st[s]++; else GERR(g, SB_ERR_OVERFLOW);
+}
 SBD_FI void st_remove(G& g, int id, int s) { if (g.e[id].st[s]) g.e[id].st[s]--; else GERR(g, SB_ERR_INDEX); }
 SBD_FI void v_freeze(G& g, int id) { st_add(g, id, SB_ST_FROZEN); }
 SBD_FI void v_poison(G& g, int id) { if (g.e[id].st[SB_ST_VITALIZED]) st_remove(g, id, SB_ST_VITALIZED); st_add(g, id, SB_ST_POISONED); }
@@ -825,6 +827,84 @@ SBD_NI int legal_mask(const G& g, u32* m) {
   return n;
 }
 SBD_FI bool have_winner(const G& g) { return g.pl[0].base < 0 || g.pl[1].base < 0; }
+
+// ---------------------------------------------------------------- scripted opponent (games/stormbound.py:563-637)
+// Draws its choices from the GAME's stream (self.random), so it advances g.draw.
+SBD_FI bool mask_any(const u32* m, int lo, int hi) {  // any legal action in [lo, hi]
+  #pragma unroll 1
+  for (int a = lo; a <= hi; a++) if (m[a >> 5] >> (a & 31) & 1u) return true;
+  return false;
+}
+SBD_FI int place_action(int ci, int pt) {  // Action.to_int PLACE (games/stormbound.py:261-270): row 0 is not encodable
+  const int y = PTY(pt);
+  return (y >= 1 && y <= 4) ? 16 * ci + (4 - y) * 4 + PTX(pt) : SB_ACTION_PASS;
+}
+SBD_NI int expert_action(G& g) {
+  u32 m[SB_MASK_WORDS];
+  const Ply& p = g.pl[g.local_order];
+  legal_mask(g, m);
+  if (mask_any(m, 148, 151)) {
+    if (p.n_hand == 0) { GERR(g, SB_ERR_EMPTY_CHOICE); return SB_ACTION_PASS; }  // max([])
+    int max_cost = -1000, ns = 0;
+    i8 sel[HAND_W];
+    #pragma unroll 1
+    for (int i = 0; i < p.n_hand; i++) if (p.hand[i].cost > max_cost) max_cost = p.hand[i].cost;
+    if (max_cost > p.mana) {
+      #pragma unroll 1
+      for (int i = 0; i < p.n_hand; i++) if (p.hand[i].cost == max_cost) sel[ns++] = (i8)i;
+      return 148 + sel[rng_below(g, ns)];
+    }
+  }
+  i8 playable[4];
+  int np = 0;
+  #pragma unroll 1
+  for (int i = 0; i < 4; i++) if (mask_any(m, 16 * i, 16 * i + 15) || mask_any(m, 21 * i + 64, 21 * i + 84)) playable[np++] = (i8)i;
+  if (np == 0) return SB_ACTION_PASS;
+  bool any_eq = false;
+  int min_cost = 1 << 20, ns = 0;
+  i8 sel[4];
+  #pragma unroll 1
+  for (int k = 0; k < np; k++) { const int c = p.hand[playable[k]].cost; any_eq |= c == p.mana; min_cost = c < min_cost ? c : min_cost; }
+  const int want = any_eq ? (int)p.mana : min_cost;
+  #pragma unroll 1
+  for (int k = 0; k < np; k++) if (p.hand[playable[k]].cost == want) sel[ns++] = (i8)k;
+  const int index = playable[sel[rng_below(g, ns)]];
+  const DCard& c = CARD(g, p.hand[index].card);
+  i8 en[24], cand[48];
+  const int n = get_targets(g, g.current_order, mkT(TK_UNIT, TS_ENEMY), PT_NONE, en);
+  int nb = 0, nc = 0;
+  #pragma unroll 1
+  for (int i = 0; i < n; i++) nb += PTY(en[i]) == 4;
+  if (c.kind == KIND_SPELL) {
+    if (!(c.flags & DCF_TARGET)) return 64 + 21 * index;
+    i8 tg[24];
+    const int nt = get_targets(g, g.current_order, card_target(c), PT_NONE, tg);
+    if (nt == 0) { GERR(g, SB_ERR_EMPTY_CHOICE); return SB_ACTION_PASS; }
+    const int where = tg[rng_below(g, nt)];
+    return is_base_pt(where) ? SB_ACTION_PASS : 65 + 21 * index + (4 - PTY(where)) * 4 + PTX(where);
+  }
+  if (c.kind == KIND_UNIT && nb > 0) {  // an enemy unit stands next to the base: block beside it
+    #pragma unroll 1
+    for (int i = 0; i < n; i++) {
+      const int x = PTX(en[i]), y = PTY(en[i]);
+      if (y != 4) continue;
+      if (x > 0 && at_xy(g, x - 1, y) < 0) cand[nc++] = (i8)PT(x - 1, y);
+      else if (x < 3 && at_xy(g, x + 1, y) < 0) cand[nc++] = (i8)PT(x + 1, y);
+    }
+  } else {
+    const int fl = p.front_line;
+    #pragma unroll 1
+    for (int x = 0; x < 4; x++) if (valid_xy(x, fl) && at_xy(g, x, fl) < 0) cand[nc++] = (i8)PT(x, fl);
+    #pragma unroll 1
+    for (int i = 0; i < n; i++) {
+      const int x = PTX(en[i]), y = PTY(en[i]);
+      if (x > 0 && y >= fl && at_xy(g, x - 1, y) < 0) cand[nc++] = (i8)PT(x - 1, y);
+      else if (x < 3 && y >= fl && at_xy(g, x + 1, y) < 0) cand[nc++] = (i8)PT(x + 1, y);
+      else if (y < 4 && y + 1 >= fl && at_xy(g, x, y + 1) < 0) cand[nc++] = (i8)PT(x, y + 1);
+    }
+  }
+  return nc > 0 ? place_action(index, cand[rng_below(g, nc)]) : SB_ACTION_PASS;
+}
 
 SBD_NI void game_step(G& g, int action) {
   Ply& p = g.pl[g.local_order];

@@ -3,6 +3,7 @@
 // Kernels
 //   k_reset            one game per thread: shuffle, weights, opening hands (games/stormbound.py:293-304)
 //   k_legal_mask       one game per thread -> 156-bit mask (games/stormbound.py:528-557)
+//   k_expert_action    one game per thread: the scripted opponent (games/stormbound.py:563-637)
 //   k_step             one game per thread: unpack, Stormbound.step, pack, fused next legal mask
 //   k_observe/k_features  one game per thread
 //   k_rollout_random   one game per thread, whole rollout in one launch (state never leaves the SM)
@@ -85,6 +86,23 @@ __global__ void __launch_bounds__(TPB_GAME) k_legal_mask(int n, const u8* states
   u32 m[SB_MASK_WORDS];
   legal_mask(g, m);
   for (int k = 0; k < SB_MASK_WORDS; k++) masks[(size_t)i * SB_MASK_WORDS + k] = m[k];
+}
+
+// Stormbound.expert_action: only the stream position (and a possible error code) change in the record.
+__global__ void __launch_bounds__(TPB_GAME) k_expert_action(int n, u8* states, u8* actions, const DCard* cards, const double* wt) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  stage_cards(s_cards, cards);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G g;
+  init_g(g, s_cards, wt);
+  __align__(16) SbState s;
+  load_state(s, states + (size_t)i * SB_STATE_BYTES);
+  unpack(g, s);
+  actions[i] = (u8)expert_action(g);
+  SbState* out = reinterpret_cast<SbState*>(states + (size_t)i * SB_STATE_BYTES);
+  out->draw = g.draw;
+  out->err = g.err;
 }
 
 __global__ void __launch_bounds__(TPB_GAME) k_step(int n, u8* states, const u8* actions, i8* reward, u8* done, u8* err,
@@ -546,6 +564,12 @@ int sb_reset(SbHandle* h, int n, const uint64_t* seeds_d, const uint8_t* decks_d
 int sb_legal_mask(SbHandle* h, int n, const uint8_t* states_d, uint32_t* masks_d, void* stream) {
   if (n <= 0) return 0;
   k_legal_mask<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, masks_d, h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_expert_action(SbHandle* h, int n, uint8_t* states_d, uint8_t* actions_d, void* stream) {
+  if (n <= 0) return 0;
+  k_expert_action<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, actions_d, h->d_cards, h->d_wt);
   LAUNCH_CHECK();
   return 0;
 }

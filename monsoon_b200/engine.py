@@ -140,6 +140,13 @@ class Engine:
                                               self._p(scores), self._stream()), "sb_select_action")
         return actions, scores
 
+    def expert_action(self, states):
+        """Stormbound.expert_action per game; advances each state's random-stream draw counter in place."""
+        n = states.shape[0]
+        actions = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.sb_expert_action(self.h, n, self._p(states), self._p(actions), self._stream()), "sb_expert_action")
+        return actions
+
     def rollout_random(self, states, max_steps=400, chain=None):
         n = states.shape[0]
         steps = torch.empty(n, dtype=torch.int32, device=self.device)

@@ -58,6 +58,10 @@ class BatchedGames:
     def observe(self):
         return self.eng.observe(self.states)
 
+    def expert_actions(self):
+        """Stormbound.expert_action for every game (u8[n]); consumes draws of each game's stream like the reference."""
+        return self.eng.expert_action(self.states)
+
     def to_play(self):
         # Stormbound.to_play: 0 if player == 1 else 1 (games/stormbound.py:312-313); player_sign is byte 16
         return (self.states[:, 16].view(torch.int8) != 1).to(torch.int64)
@@ -107,6 +111,9 @@ class _Env:
 
     def legal_actions(self):
         return self._g.legal_actions()
+
+    def expert_action(self):
+        return self._g.expert_agent()
 
     def to_play(self):
         return self._g.to_play()
@@ -185,7 +192,13 @@ class Game:
         return int(input("action (0-155): "))
 
     def expert_agent(self):
-        raise NotImplementedError("expert_action is row f3 of SURVEY.md 8(f) (next, not in this round)")
+        """games/stormbound.py:201-209 -> Stormbound.expert_action (:563-637); draws from the game's own stream."""
+        a = self.eng.expert_action(self.state)
+        self._host_cache = None
+        err = int(self._host()[18])
+        if err:
+            raise EngineError(err)
+        return int(a[0])
 
     def action_to_string(self, action_number):
         return self._action_names[action_number]

@@ -196,8 +196,12 @@ def card_index(card):
 
 def _status_word(unit):
     w = 0
+    counts = [0] * 5
     for s in unit.status_effects:
+        counts[int(s)] += 1
         w += 1 << (ST_BITS * int(s))
+    if max(counts) > 63:
+        raise PackOverflow("status counter")  # 64 copies of one status do not fit the 6-bit field
     return w
 
 
@@ -381,3 +385,43 @@ def play_random_game(seed, decks=None, factions=None, max_steps=400, record=True
                 masks=np.array(masks, dtype=np.uint32).reshape(-1, 5),
                 digests=np.array(digests, dtype=np.uint64), states=states, err=err, final=final,
                 n_steps=step, done=bool(done), game=game)
+
+
+def play_expert_game(seed, decks=None, factions=None, max_steps=400, record=True):
+    """Both seats play Stormbound.expert_action (games/stormbound.py:563-637), which draws its choices from
+    the GAME's stream.  Same tape layout as play_random_game, without masks."""
+    game = make_game(seed, decks, factions)
+    init = pack_reference(game)
+    actions, digests, states = [], [], []
+    err = 0
+    done = False
+    step = 0
+    with quiet():
+        while not done and step < max_steps:
+            try:
+                a = game.env.expert_action()
+            except Exception:  # noqa: BLE001 -- choice([]) / max([]) inside expert_action itself
+                err = 3
+                break
+            try:
+                _obs, reward, done = game.step(a)
+            except Exception:  # noqa: BLE001
+                err = 1
+                actions.append(a)
+                break
+            step += 1
+            try:
+                st = pack_reference(game, steps=step, done=(1 if done else 0) | (2 if reward else 0))
+            except PackOverflow:
+                err = 2
+                step -= 1
+                actions.append(a)
+                break
+            actions.append(a)
+            digests.append(fnv1a64(st.tobytes()))
+            if record:
+                states.append(st)
+    return dict(seed=seed, init=init, actions=np.array(actions, dtype=np.uint8),
+                digests=np.array(digests, dtype=np.uint64), states=states, err=err,
+                n_steps=step, done=bool(done), game=game)
+

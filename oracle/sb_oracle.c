@@ -280,7 +280,9 @@ void o_spell_ability(Game *g, int card, int caster, int pos_pt) {
 }
 
 /* ------------------------------------------------------------------ status verbs (unit.py:239-275) */
-void o_st_add(Game *g, int id, int st) { g->e[id].st[st]++; }
+void o_st_add(Game *g, int id, int st) { /* 6-bit packed counters: the 64th copy of one status flags the game */
+  if (g->e[id].st[st] < 63) g->e[id].st[st]++; else ERR(g, SB_ERR_OVERFLOW);
+}
 void o_st_remove(Game *g, int id, int st) { /* list.remove raises ValueError if absent */
   if (g->e[id].st[st] > 0) g->e[id].st[st]--; else ERR(g, SB_ERR_INDEX);
 }
@@ -685,6 +687,72 @@ static int legal_mask(Game *g, uint32_t m[SB_MASK_WORDS]) {
 }
 static int have_winner(Game *g) { return g->pl[0].base < 0 || g->pl[1].base < 0; }
 
+/* ------------------------------------------------------------------ scripted opponent (games/stormbound.py:563-637) */
+static int mask_has_range(const uint32_t *m, int lo, int hi) {
+  for (int a = lo; a <= hi; a++) if (m[a >> 5] >> (a & 31) & 1) return 1;
+  return 0;
+}
+static int place_action(int ci, int pt) { /* Action.to_int PLACE (games/stormbound.py:261-270); row 0 is not encodable -> 155 */
+  int x = PTX(pt), y = PTY(pt);
+  return (y >= 1 && y <= 4) ? 16 * ci + (4 - y) * 4 + x : SB_ACTION_PASS;
+}
+static int expert_action(Game *g) {
+  uint32_t m[SB_MASK_WORDS];
+  Ply *p = o_local(g);
+  int pts[24], n;
+  legal_mask(g, m);
+  if (mask_has_range(m, 148, 151)) {
+    int max_cost = -1000, sel[SB_HAND_MAX + 2], ns = 0;
+    if (p->n_hand == 0) { ERR(g, SB_ERR_EMPTY_CHOICE); return SB_ACTION_PASS; } /* max([]) */
+    for (int i = 0; i < p->n_hand; i++) if (p->hand[i].cost > max_cost) max_cost = p->hand[i].cost;
+    if (max_cost > p->mana) {
+      for (int i = 0; i < p->n_hand; i++) if (p->hand[i].cost == max_cost) sel[ns++] = i;
+      return 148 + sel[o_rng_below(g, ns)];
+    }
+  }
+  int playable[4], np = 0;
+  for (int i = 0; i < 4; i++) if (mask_has_range(m, 16 * i, 16 * i + 15) || mask_has_range(m, 21 * i + 64, 21 * i + 84)) playable[np++] = i;
+  if (np > 0) {
+    int sel[4], ns = 0, any_eq = 0, min_cost = 1 << 30;
+    for (int k = 0; k < np; k++) { int c = p->hand[playable[k]].cost; if (c == p->mana) any_eq = 1; if (c < min_cost) min_cost = c; }
+    for (int k = 0; k < np; k++) if (p->hand[playable[k]].cost == (any_eq ? p->mana : min_cost)) sel[ns++] = k;
+    int index = playable[sel[o_rng_below(g, ns)]];
+    const OCard *c = &OCARDS[p->hand[index].card];
+    static const Target T_UNIT_E = {TK_UNIT, TS_ENEMY, 0, 0, 0, 0, 0, 0, 0, 0};
+    int bbe[24], nb = 0;
+    n = o_get_targets(g, g->current_order, &T_UNIT_E, PT_NONE, pts);
+    for (int i = 0; i < n; i++) if (PTY(pts[i]) == 4) bbe[nb++] = pts[i];
+    if (c->kind == KIND_SPELL) {
+      if (!c->has_target) return 64 + 21 * index;
+      Target t = {c->t_kind, c->t_side, c->t_types, c->t_xtypes, c->t_status, c->t_xstatus, c->t_limit >= 0, c->t_limit, c->t_nonhero, c->t_base};
+      int tg[24], nt = o_get_targets(g, g->current_order, &t, PT_NONE, tg);
+      if (nt == 0) { ERR(g, SB_ERR_EMPTY_CHOICE); return SB_ACTION_PASS; }
+      int where = tg[o_rng_below(g, nt)];
+      if (is_base_pt(where)) return SB_ACTION_PASS;
+      return 65 + 21 * index + (4 - PTY(where)) * 4 + PTX(where);
+    } else if (c->kind == KIND_UNIT && nb > 0) {
+      int cand[24], nc = 0;
+      for (int i = 0; i < nb; i++) {
+        int x = PTX(bbe[i]), y = PTY(bbe[i]);
+        if (x > 0 && o_at(g, x - 1, y) < 0) cand[nc++] = PT(x - 1, y);
+        else if (x < 3 && o_at(g, x + 1, y) < 0) cand[nc++] = PT(x + 1, y);
+      }
+      if (nc > 0) return place_action(index, cand[o_rng_below(g, nc)]);
+    } else {
+      int cand[48], nc = 0, fl = p->front_line;
+      for (int x = 0; x < 4; x++) if (o_at(g, x, fl) < 0 && valid_xy(x, fl)) cand[nc++] = PT(x, fl);
+      for (int i = 0; i < n; i++) {
+        int x = PTX(pts[i]), y = PTY(pts[i]);
+        if (x > 0 && y >= fl && o_at(g, x - 1, y) < 0) cand[nc++] = PT(x - 1, y);
+        else if (x < 3 && y >= fl && o_at(g, x + 1, y) < 0) cand[nc++] = PT(x + 1, y);
+        else if (y < 4 && y + 1 >= fl && o_at(g, x, y + 1) < 0) cand[nc++] = PT(x, y + 1);
+      }
+      if (nc > 0) return place_action(index, cand[o_rng_below(g, nc)]);
+    }
+  }
+  return SB_ACTION_PASS;
+}
+
 static void game_step(Game *g, int action) {
   Ply *p = o_local(g);
   if (action < 64) {
@@ -902,6 +970,15 @@ uint64_t sbo_digest(const SbState *s) {
   uint64_t h = 0xCBF29CE484222325ull;
   for (int i = 0; i < (int)sizeof(SbState); i++) { h ^= b[i]; h *= 0x100000001B3ull; }
   return h;
+}
+/* Stormbound.expert_action: returns the action, advances the game's random stream in *s (it draws from it). */
+int sbo_expert_action(SbState *s) {
+  Game *g = (Game *)malloc(sizeof(Game));
+  o_unpack(g, s);
+  int a = expert_action(g);
+  o_pack(g, s);
+  free(g);
+  return a;
 }
 /* Uniform-random agent rollout of one game (config 2).  digests/actions may be NULL.  Returns steps. */
 int sbo_rollout_random(SbState *s, int max_steps, uint8_t *actions, uint64_t *digests, uint32_t *masks) {

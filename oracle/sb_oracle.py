@@ -52,6 +52,8 @@ def lib():
         L.sbo_batch_random.restype = ctypes.c_long
         L.sbo_batch_heuristic.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]
         L.sbo_batch_heuristic.restype = ctypes.c_long
+        L.sbo_expert_action.argtypes = [vp]
+        L.sbo_expert_action.restype = ctypes.c_int
         L.sbo_agent_pick.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]
         L.sbo_agent_pick.restype = ctypes.c_uint32
         assert L.sbo_state_bytes() == S
@@ -81,6 +83,11 @@ def legal_mask(st):
 def step(st, action):
     lib().sbo_step(_p(st), int(action))
     return st
+
+
+def expert_action(st):
+    """Stormbound.expert_action (games/stormbound.py:563-637); advances the random stream stored in st."""
+    return int(lib().sbo_expert_action(_p(st)))
 
 
 def digest(st):

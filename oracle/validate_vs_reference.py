@@ -121,3 +121,35 @@ def main():
 
 if __name__ == "__main__":
     sys.exit(main())
+
+
+def check_expert_seed(seed, decks=None, factions=None, max_steps=400):
+    """Both seats play Stormbound.expert_action (it draws from the game's stream): every action and every packed
+    state must match the oracle's sbo_expert_action + sbo_step; a reference exception must flag the oracle game."""
+    r = h.ref()
+    decks = decks or h.DEFAULT_DECKS
+    factions = factions or h.DEFAULT_FACTIONS
+    tape = h.play_expert_game(seed, decks, factions, max_steps=max_steps)
+    st = o.new_game(seed, [r.index[n] for n in decks[0]], [r.index[n] for n in decks[1]], factions[0], factions[1])
+    for k in range(tape["n_steps"]):
+        a = o.expert_action(st)
+        if a != tape["actions"][k]:
+            print("seed", seed, "step", k, "EXPERT action ref", tape["actions"][k], "oracle", a)
+            return False, k, tape
+        o.step(st, a)
+        if st[18] == 5:
+            return True, k, tape
+        if st.tobytes() != tape["states"][k].tobytes():
+            print("seed", seed, "step", k, "action", a, "STATE mismatch", diff_states(tape["states"][k], st)[:6])
+            return False, k, tape
+    if tape["err"]:
+        a = o.expert_action(st)
+        if tape["err"] != 3:
+            if a != tape["actions"][-1]:
+                print("seed", seed, "last action ref", tape["actions"][-1], "oracle", a)
+                return False, tape["n_steps"], tape
+            o.step(st, a)
+        if not st[18]:
+            print("seed", seed, "reference raised (kind %d) at step" % tape["err"], tape["n_steps"], "oracle did not")
+            return False, tape["n_steps"], tape
+    return True, tape["n_steps"], tape

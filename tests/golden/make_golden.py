@@ -14,6 +14,8 @@ HeuristicAgent), then serialised with pack_reference.  Files:
                         excluded): decks, factions, steps, chain, final digest, outcome kind
   heuristic_decisions.npz  states sampled from reference HeuristicAgent-vs-HeuristicAgent games with the
                         reference's per-action scores, legal set and chosen action, plus whole-game results
+  expert_tapes.npz      both seats play the reference's Stormbound.expert_action (it draws from the game's stream):
+                        160 default-deck + 240 random-deck games, per-step actions and state digests
 """
 import argparse
 import multiprocessing as mp
@@ -116,10 +118,22 @@ def work_heur(seed):
     return seed, w1, w2, np.array(actions, dtype=np.uint8), result, h.fnv1a64(final.tobytes()), samples
 
 
+def work_expert(seed):
+    import ref_harness as h
+    r = h.ref()
+    if seed < 200000:
+        decks, factions = h.DEFAULT_DECKS, h.DEFAULT_FACTIONS
+    else:
+        decks, factions = random_decks(seed)
+    t = h.play_expert_game(seed, decks, factions, record=False)
+    return (seed, [[r.index[n] for n in d] for d in decks], list(factions), np.frombuffer(t["init"].tobytes(), dtype=np.uint8),
+            t["actions"], t["digests"], t["n_steps"], t["err"], int(t["done"]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--procs", type=int, default=os.cpu_count())
-    ap.add_argument("--only", default="tapes,chain,rand,heur")
+    ap.add_argument("--only", default="tapes,chain,rand,heur,expert")
     ap.add_argument("--n-chain", type=int, default=10000)
     ap.add_argument("--n-rand", type=int, default=3000)
     ap.add_argument("--n-heur", type=int, default=24)
@@ -168,6 +182,15 @@ def main():
                             weights=np.stack([s[1] for s in samples]), masks=np.stack([s[2] for s in samples]),
                             scores=np.stack([s[3] for s in samples]), chosen=np.array([s[4] for s in samples], dtype=np.uint8))
         print("heuristic_decisions.npz games", len(res), "samples", len(samples))
+    if "expert" in only:
+        res = pool.map(work_expert, list(range(160)) + list(range(200000, 200240)), chunksize=4)
+        np.savez_compressed(os.path.join(HERE, "expert_tapes.npz"),
+                            seeds=np.array([r[0] for r in res], dtype=np.uint64), decks=np.array([r[1] for r in res], dtype=np.uint8),
+                            factions=np.array([r[2] for r in res], dtype=np.uint8), init=np.stack([r[3] for r in res]),
+                            lengths=np.array([len(r[4]) for r in res], dtype=np.int32), actions=np.concatenate([r[4] for r in res]),
+                            steps=np.array([r[6] for r in res], dtype=np.int32), digests=np.concatenate([r[5] for r in res]),
+                            err=np.array([r[7] for r in res], dtype=np.uint8), done=np.array([r[8] for r in res], dtype=np.uint8))
+        print("expert_tapes.npz", len(res), "ref exceptions", sum(1 for r in res if r[7] in (1, 3)), "overflow", sum(1 for r in res if r[7] == 2))
 
 
 if __name__ == "__main__":

@@ -47,6 +47,57 @@ def test_random_deck_games_rollout_kernel(engine):
     assert unsupported.sum() <= len(unsupported) * 3 // 200
 
 
+def fnv1a64_rows(rows):
+    """fnv1a64 of every 512-byte row (the digest the fixtures store), vectorised over games"""
+    h = np.full(rows.shape[0], 0xCBF29CE484222325, dtype=np.uint64)
+    prime = np.uint64(0x100000001B3)
+    with np.errstate(over="ignore"):
+        for b in range(rows.shape[1]):
+            h = (h ^ rows[:, b].astype(np.uint64)) * prime
+    return h
+
+
+def test_expert_games_step_api(engine):
+    """sb_expert_action + sb_step against the reference's expert-vs-expert tapes: every action, every state digest."""
+    z = load("expert_tapes.npz")
+    dev = engine.device
+    n = len(z["seeds"])
+    st = engine.reset(torch.from_numpy(z["seeds"].astype(np.int64)).to(dev), torch.from_numpy(z["decks"]).to(dev),
+                      torch.from_numpy(z["factions"]).to(dev))
+    assert np.array_equal(st.cpu().numpy(), z["init"])
+    steps, lengths = z["steps"].astype(np.int64), z["lengths"].astype(np.int64)
+    aoff = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+    doff = np.concatenate([[0], np.cumsum(steps)[:-1]])
+    tolerated = np.zeros(n, dtype=bool)
+    raised = np.zeros(n, dtype=bool)
+    for k in range(int(lengths.max()) + 1):
+        # games still inside their tape; a game the reference aborted gets its aborting action (or expert call) too
+        live = np.nonzero(((k < steps) | ((k == steps) & (z["err"] != 0))) & ~tolerated)[0]
+        if live.size == 0:
+            break
+        idx = torch.from_numpy(live).to(dev)
+        sub = st.index_select(0, idx).contiguous()
+        act = engine.expert_action(sub)
+        a = act.cpu().numpy()
+        expert_err = sub[:, 18].cpu().numpy() != 0
+        _r, _d, err = engine.step(sub, act)
+        st.index_copy_(0, idx, sub)
+        host, err = sub.cpu().numpy(), err.cpu().numpy()
+        inside = k < steps[live]
+        tolerated[live[inside & ((err == 5) | (err == 6))]] = True
+        chk = inside & (err != 5) & (err != 6)
+        g = live[chk]
+        assert np.array_equal(a[chk], z["actions"][aoff[g] + k]), k
+        assert np.array_equal(fnv1a64_rows(host[chk]), z["digests"][doff[g] + k]), k
+        last = live[~inside]
+        kinds = z["err"][last]
+        same_action = (kinds == 3) | (a[~inside] == z["actions"][np.minimum(aoff[last] + k, len(z["actions"]) - 1)])
+        assert same_action.all(), k
+        raised[last] = (err[~inside] != 0) | expert_err[~inside]
+    assert raised[(z["err"] != 0) & ~tolerated].all()
+    assert tolerated.sum() <= n * 3 // 200
+
+
 def test_heuristic_decisions(engine):
     z = load("heuristic_decisions.npz")
     st = torch.from_numpy(z["states"]).to(engine.device)
