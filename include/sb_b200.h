@@ -33,9 +33,12 @@ int sb_destroy(SbHandle *h);
 const char *sb_last_error(SbHandle *h);
 int sb_device(SbHandle *h);
 int sb_sm_count(SbHandle *h);
-/* tuning knobs for the rollout kernels: "games_per_warp" = 0 (auto by batch size) or 1..32 consecutive lanes
- * of every warp that carry a game; "lanes_per_game" = 2..32 selects the lane-group shape (working set in
- * shared memory) instead. */
+/* tuning knobs for the rollout kernels (all default to "auto by batch size"): "games_per_warp" = 0 (auto) or
+ * 1..32 consecutive lanes of every warp that carry a game; "turn_sync" 0/1; "block_sync" = -1 auto, 0, or the
+ * CTA size (128..1024) whose warps change phase together; "refill" = -1 auto, 0/1: finished lanes of the random
+ * rollout take the next game from a counter ("refill_ctas" persistent CTAs per SM, "refill_grid" CTAs in total,
+ * 0 = auto); "heur_wpc" = warps per CTA of the heuristic rollout;
+ * "lanes_per_game" is accepted and ignored (retired shape). */
 int sb_set_option(SbHandle *h, const char *key, int value);
 /* kernels launched through this handle so far (bench.py's gpu_launches) */
 uint64_t sb_launch_count(SbHandle *h);
@@ -66,6 +69,18 @@ int sb_features(SbHandle *h, int n, const uint8_t *states_d, double *feat_d, uin
  * NaN for illegal actions.  One warp per game, one lane per candidate action. */
 int sb_select_action(SbHandle *h, int n, const uint8_t *states_d, const double *weights_d, uint8_t *actions_d,
                      double *scores_d, void *stream);
+
+/* DeckEvolutionConfig.get_deck_configuration / generate_random_deck (utils.py:26-119,121-241) for n games: game g
+ * draws from philox(counter=(draw, generation, 0xDEC4, 0), key=seeds_d[g]) with CPython's random.sample call
+ * shape.  mode 0 exploit (archetypes verbatim), 1 explore (n_preserve = min(int(12*preserve_ratio), 12) cards
+ * sampled from the archetype, the rest from own faction + NEUTRAL), 2 balance (random() < q keeps the archetype,
+ * drawn for both seats first), 3 fully random decks for per-game factions_d u8[n,2] (BASELINE config 5).
+ * archetypes u8[2][12] card ids and arch_factions u8[2] are HOST pointers (the config object's fields);
+ * factions_d nullable (= arch_factions for every game); decks_d u8[n,2,12]; factions_out_d nullable u8[n,2].
+ * The outputs feed sb_reset(decks_d, 12, 0, factions). */
+int sb_generate_decks(SbHandle *h, int n, const uint64_t *seeds_d, uint32_t generation, int mode, int n_preserve, double q,
+                      const uint8_t *archetypes, const uint8_t *arch_factions, const uint8_t *factions_d, uint8_t *decks_d,
+                      uint8_t *factions_out_d, void *stream);
 
 /* Stormbound.expert_action (games/stormbound.py:563-637) for n games: the scripted opponent behind
  * Game.expert_agent (games/stormbound.py:201-209).  It draws its choices from the GAME's stream, so each

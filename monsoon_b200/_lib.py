@@ -32,6 +32,7 @@ SIGNATURES = {
     "sb_observe": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "sb_features": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "sb_select_action": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    "sb_generate_decks": (_int, [_vp, _int, _vp, ctypes.c_uint32, _int, _int, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_expert_action": (_int, [_vp, _int, _vp, _vp, _vp]),
     "sb_rollout_random": (_int, [_vp, _int, _vp, _int, _vp, _vp, _vp]),
     "sb_rollout_heuristic": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),

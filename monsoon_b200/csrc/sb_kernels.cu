@@ -2,6 +2,7 @@
 //
 // Kernels
 //   k_reset            one game per thread: shuffle, weights, opening hands (games/stormbound.py:293-304)
+//   k_generate_decks   one game per thread: both decks of DeckEvolutionConfig.get_deck_configuration (utils.py:26-241)
 //   k_legal_mask       one game per thread -> 156-bit mask (games/stormbound.py:528-557)
 //   k_expert_action    one game per thread: the scripted opponent (games/stormbound.py:563-637)
 //   k_step             one game per thread: unpack, Stormbound.step, pack, fused next legal mask
@@ -71,6 +72,71 @@ __global__ void __launch_bounds__(TPB_GAME) k_reset(int n, const unsigned long l
   }
   pack(g, s);
   store_state(states + (size_t)i * SB_STATE_BYTES, s);
+}
+
+// ---------------------------------------------------------------- deck generation (utils.py:26-241)
+// One game per thread draws both decks from its own stream: philox(counter=(draw, generation, 0xDEC4, 0), key=seed).
+// random.sample call shape of CPython 3.12: pool method while n <= setsize, else the rejection-set method.
+struct DeckRng { u32 lo, hi, gen, draw; };
+SBD_FI int deck_below(DeckRng& r, int n) {
+  u32 w0, w1;
+  philox(r.draw++, r.gen, 0xDEC4u, 0u, r.lo, r.hi, w0, w1);
+  return (int)__umulhi(w0, (u32)n);
+}
+SBD_FI double deck_random(DeckRng& r) {
+  u32 w0, w1;
+  philox(r.draw++, r.gen, 0xDEC4u, 0u, r.lo, r.hi, w0, w1);
+  return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) / 9007199254740992.0;
+}
+#define POOL_W 80  // own faction + NEUTRAL: 70..74 of the 112 cards
+SBD void py_sample(DeckRng& r, const u8* pop, int n, int k, u8* out) {
+  int setsize = 21;
+  if (k > 5) { int p = 1; while (p < 3 * k) p *= 4; setsize += p; }
+  if (n <= setsize) {
+    u8 pool[POOL_W];
+    for (int i = 0; i < n; i++) pool[i] = pop[i];
+    for (int i = 0; i < k; i++) { const int j = deck_below(r, n - i); out[i] = pool[j]; pool[j] = pool[n - i - 1]; }
+  } else {
+    u32 taken[(POOL_W + 31) / 32] = {0, 0, 0};
+    for (int i = 0; i < k; i++) {
+      int j = deck_below(r, n);
+      while (taken[j >> 5] >> (j & 31) & 1u) j = deck_below(r, n);
+      taken[j >> 5] |= 1u << (j & 31);
+      out[i] = pop[j];
+    }
+  }
+}
+SBD void random_deck(DeckRng& r, const u8* pool, int n_pool, const u8* original, int n_preserve, u8* deck) {
+  if (n_preserve >= 12) { for (int i = 0; i < 12; i++) deck[i] = original[i]; return; }
+  if (n_preserve > 0) py_sample(r, original, 12, n_preserve, deck); else n_preserve = 0;
+  py_sample(r, pool, n_pool, 12 - n_preserve, deck + n_preserve);
+}
+// pools: [5][POOL_W] card ids per faction (row 0 = NEUTRAL only), pool_n[5]; factions: per game [n][2] or one shared pair
+__global__ void __launch_bounds__(128) k_generate_decks(int n, const unsigned long long* seeds, u32 generation, int mode, int n_preserve,
+                                                       double q, const u8* archetypes, const u8* factions, int factions_shared,
+                                                       const u8* pools, const int* pool_n, u8* decks, u8* factions_out) {
+  __shared__ u8 s_pool[5 * POOL_W];
+  __shared__ int s_pn[5];
+  __shared__ u8 s_arch[24];
+  for (int i = threadIdx.x; i < 5 * POOL_W; i += blockDim.x) s_pool[i] = pools[i];
+  if (threadIdx.x < 5) s_pn[threadIdx.x] = pool_n[threadIdx.x];
+  if (threadIdx.x < 24) s_arch[threadIdx.x] = archetypes[threadIdx.x];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long seed = seeds[i];
+  DeckRng r = {(u32)seed, (u32)(seed >> 32), generation, 0u};
+  const u8* fc = factions + (factions_shared ? 0 : (size_t)i * 2);
+  u8 d[24];
+  bool keep[2] = {false, false};
+  if (mode == 2) { keep[0] = deck_random(r) < q; keep[1] = deck_random(r) < q; }  // both drawn before any deck (utils.py:207-208)
+  for (int o = 0; o < 2; o++) {
+    const int f = fc[o] <= 4 ? fc[o] : 0;
+    if (mode == 0 || (mode == 2 && keep[o])) { for (int k = 0; k < 12; k++) d[12 * o + k] = s_arch[12 * o + k]; }
+    else random_deck(r, s_pool + f * POOL_W, s_pn[f], s_arch + 12 * o, mode == 1 ? n_preserve : 0, d + 12 * o);
+  }
+  for (int k = 0; k < 24; k++) decks[(size_t)i * 24 + k] = d[k];
+  if (factions_out) { factions_out[(size_t)i * 2] = fc[0]; factions_out[(size_t)i * 2 + 1] = fc[1]; }
 }
 
 __global__ void __launch_bounds__(TPB_GAME) k_legal_mask(int n, const u8* states, u32* masks, const DCard* cards, const double* wt) {
@@ -186,26 +252,27 @@ SBD_FI int pick_action(const G& g) {
 template <bool DIGEST, int TPB, bool BSYNC>
 __global__ void __launch_bounds__(TPB) k_rollout_random(int n, u8* states, int max_steps, int* steps_out,
                                                         unsigned long long* chain, const DCard* cards, const double* wt,
-                                                        int gpw, int turn_sync) {
+                                                        int gpw, int turn_sync, int* queue) {
   __shared__ DCard s_cards[SBC_COUNT];
   stage_cards(s_cards, cards);
   // gpw games per warp on CONSECUTIVE lanes (32 = plain thread per game).  Fewer games per warp = fewer
   // divergent paths serialised on one scheduler slot when the batch is small; consecutive lanes keep the
   // 32-byte local-memory sectors of the thread-private working set dense.  All 32 lanes stay in the kernel
   // (full-mask votes below); lanes without a game just never become `alive`.
+  // queue != nullptr (batches larger than the resident lanes): a lane whose game ended takes the next game
+  // index from a global counter instead of idling until the longest game of its CTA is over.
   const unsigned FULL = 0xFFFFFFFFu;
   const int lane = threadIdx.x & 31;
-  const int i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * gpw + lane;
-  const bool has_game = lane < gpw && i < n;
+  int i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * gpw + lane;
+  bool has_game = !queue && lane < gpw && i < n;
   G g;
   init_g(g, s_cards, wt);
   __align__(16) SbState s;  // 128-bit moves
-  u8* sp = states + (size_t)(has_game ? i : 0) * SB_STATE_BYTES;
   unsigned long long ch = 0ull;
   int k = 0;
   bool alive = false;
   if (has_game) {
-    load_state(s, sp);
+    load_state(s, states + (size_t)i * SB_STATE_BYTES);
     unpack(g, s);
     if (DIGEST) ch = chain[i];
     alive = !(g.done & SB_DONE) && !g.err && max_steps > 0;
@@ -220,7 +287,37 @@ __global__ void __launch_bounds__(TPB) k_rollout_random(int n, u8* states, int m
     }
   } else {
     bool at_pass = false;
-    while (BSYNC ? __syncthreads_or(alive) : __any_sync(FULL, alive)) {
+    bool dry = queue == nullptr;  // no more games to take
+    for (;;) {
+      if (!dry) {  // warp-converged here (after the vote at the bottom of the previous round)
+        const unsigned want = __ballot_sync(FULL, !alive);
+        if (want) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(queue, __popc(want));
+          base = __shfl_sync(FULL, base, 0);
+          if (!alive) {
+            if (has_game) {  // retire the finished game
+              pack(g, s);
+              store_state(states + (size_t)i * SB_STATE_BYTES, s);
+              if (steps_out) steps_out[i] = k;
+              if (DIGEST) chain[i] = ch;
+              has_game = false;
+            }
+            i = base + __popc(want & ((1u << lane) - 1u));
+            if (i < n) {
+              has_game = true;
+              load_state(s, states + (size_t)i * SB_STATE_BYTES);
+              unpack(g, s);
+              ch = DIGEST ? chain[i] : 0ull;
+              k = 0;
+              at_pass = false;
+              alive = !(g.done & SB_DONE) && !g.err && max_steps > 0;
+            }
+          }
+          dry = base + __popc(want) >= n;  // warp-uniform
+        }
+      }
+      if (!(BSYNC ? __syncthreads_or(alive) : __any_sync(FULL, alive))) break;
       for (;;) {  // phase A: non-PASS actions
         int a = -1;
         if (alive && !at_pass) {
@@ -248,7 +345,7 @@ __global__ void __launch_bounds__(TPB) k_rollout_random(int n, u8* states, int m
   }
   if (has_game) {
     pack(g, s);
-    store_state(sp, s);
+    store_state(states + (size_t)i * SB_STATE_BYTES, s);
     if (steps_out) steps_out[i] = k;
     if (DIGEST) chain[i] = ch;
   }
@@ -430,6 +527,13 @@ struct SbHandle {
   int block_sync;  // 0, or 128/256/512: CTA size whose warps change phase together (CTA-wide votes)
   int heur_wpc;    // heuristic rollout: 4 (independent warps) or 8/16/32 warps per CTA deciding in step
   int ctas_per_sm;
+  int refill;      // -1 auto, 0 off, 1 on: finished lanes of the random rollout take the next game from a counter
+  int refill_ctas; // persistent CTAs per SM in refill mode (0 = 1024 threads per SM)
+  int refill_grid; // persistent CTAs in total (tests: a grid much smaller than the batch); 0 = sm_count x refill_ctas
+  int* d_queue;
+  u8* d_pools;    // deck generation: [5][POOL_W] card ids per faction
+  int* d_pool_n;
+  u8* d_arch;     // staged archetypes [24] + factions [2]
 };
 
 static int fail(SbHandle* h, cudaError_t e, const char* what) {
@@ -453,17 +557,30 @@ static void launch_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max
   unsigned long long* ch = (unsigned long long*)chain_d;
   int bs = h->block_sync;
   if (bs < 0) bs = n >= 196608 ? 1024 : n >= 49152 ? 512 : 0;  // auto (tools/sweep_bsync.py): pays off once the chip is full
+  // lane refill: persistent grid of resident CTAs, lanes take games from a counter (batches beyond the resident lanes)
+  int* q = nullptr;
+  const int resident = h->sm_count * 1024;  // 64 registers x 1024 threads fill one SM's register file
+  int refill = h->refill;
+  if (refill < 0) refill = n >= resident + resident / 4;
+  if (refill && bs >= 128 && h->turn_sync && gpw == 32) {
+    q = h->d_queue;
+    cudaMemsetAsync(q, 0, sizeof(int), st);
+  }
+  // resident CTAs per SM of the persistent grid (0 = fill the register file: 1024 threads per SM)
+  const int tpb = bs >= 1024 ? 1024 : bs >= 512 ? 512 : bs >= 256 ? 256 : 128;
+  const int per_sm = h->refill_ctas > 0 ? h->refill_ctas : 1024 / tpb;
+  const int qgrid = h->refill_grid > 0 ? h->refill_grid : h->sm_count * per_sm;
   if (bs >= 1024 && h->turn_sync)
-    k_rollout_random<DIGEST, 1024, true><<<grid_for(n, gpw * 32), 1024, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1);
+    k_rollout_random<DIGEST, 1024, true><<<q ? qgrid : grid_for(n, gpw * 32), 1024, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1, q);
   else if (bs >= 512 && h->turn_sync)
-    k_rollout_random<DIGEST, 512, true><<<grid_for(n, gpw * 16), 512, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1);
+    k_rollout_random<DIGEST, 512, true><<<q ? qgrid : grid_for(n, gpw * 16), 512, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1, q);
   else if (bs >= 256 && h->turn_sync)
-    k_rollout_random<DIGEST, 256, true><<<grid_for(n, gpw * 8), 256, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1);
+    k_rollout_random<DIGEST, 256, true><<<q ? qgrid : grid_for(n, gpw * 8), 256, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1, q);
   else if (bs >= 128 && h->turn_sync)
-    k_rollout_random<DIGEST, 128, true><<<grid_for(n, gpw * 4), 128, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1);
+    k_rollout_random<DIGEST, 128, true><<<q ? qgrid : grid_for(n, gpw * 4), 128, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1, q);
   else
     k_rollout_random<DIGEST, TPB_GAME, false><<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, st>>>(n, states_d, max_steps, steps_d, ch,
-                                                                                                    h->d_cards, h->d_wt, gpw, h->turn_sync);
+                                                                                                    h->d_cards, h->d_wt, gpw, h->turn_sync, nullptr);
 }
 
 extern "C" {
@@ -532,6 +649,21 @@ int sb_create(int device, SbHandle** out) {
   }
   CK(cudaMalloc(&h->d_wt, sizeof wt));
   CK(cudaMemcpy(h->d_wt, wt, sizeof wt, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&h->d_queue, sizeof(int)));
+  {  // deck pools: dir(cards) order == card index order; own faction + NEUTRAL (utils.py:74-84)
+    static u8 pools[5 * POOL_W];
+    int pn[5] = {0, 0, 0, 0, 0};
+    memset(pools, 0, sizeof pools);
+    for (int f = 0; f <= 4; f++)  // f = 0: an archetype led by a NEUTRAL card gives Faction.NEUTRAL (utils.py:152-153)
+      for (int c = 1; c <= 112; c++)
+        if ((HOST_CARDS[c].faction == f || HOST_CARDS[c].faction == 0) && pn[f] < POOL_W) pools[f * POOL_W + pn[f]++] = (u8)c;
+    CK(cudaMalloc(&h->d_pools, sizeof pools));
+    CK(cudaMemcpy(h->d_pools, pools, sizeof pools, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_pool_n, sizeof pn));
+    CK(cudaMemcpy(h->d_pool_n, pn, sizeof pn, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&h->d_arch, 32));
+  }
+  h->refill = -1;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const char* env = getenv("SB_GPW");
   h->gpw = env ? atoi(env) : 0;
@@ -542,6 +674,10 @@ int sb_destroy(SbHandle* h) {
   cudaSetDevice(h->device);
   if (h->d_cards) cudaFree(h->d_cards);
   if (h->d_wt) cudaFree(h->d_wt);
+  if (h->d_queue) cudaFree(h->d_queue);
+  if (h->d_pools) cudaFree(h->d_pools);
+  if (h->d_pool_n) cudaFree(h->d_pool_n);
+  if (h->d_arch) cudaFree(h->d_arch);
   if (h->d_stage) cudaFree(h->d_stage);
   if (h->stream) cudaStreamDestroy(h->stream);
   free(h);
@@ -558,6 +694,28 @@ int sb_reset(SbHandle* h, int n, const uint64_t* seeds_d, const uint8_t* decks_d
   if (n <= 0) return 0;
   k_reset<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, (const unsigned long long*)seeds_d, decks_d, n_deck,
                                                                         decks_shared, factions_d, states_d, h->d_cards, h->d_wt);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_generate_decks(SbHandle* h, int n, const uint64_t* seeds_d, uint32_t generation, int mode, int n_preserve, double q,
+                      const uint8_t* archetypes, const uint8_t* arch_factions, const uint8_t* factions_d, uint8_t* decks_d,
+                      uint8_t* factions_out_d, void* stream) {
+  if (n <= 0) return 0;
+  if (mode < 0 || mode > 3 || (mode != 3 && (!archetypes || !arch_factions)) || (mode == 3 && !factions_d)) {
+    snprintf(h->err, sizeof h->err, "sb_generate_decks: bad mode/arguments");
+    return -1;
+  }
+  uint8_t host[32];
+  memset(host, 0, sizeof host);
+  if (archetypes) memcpy(host, archetypes, 24);
+  if (arch_factions) memcpy(host + 24, arch_factions, 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(h->d_arch, host, 32, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));  // `host` is a stack buffer
+  const bool shared = factions_d == nullptr;
+  k_generate_decks<<<grid_for(n, 128), 128, 0, st>>>(n, (const unsigned long long*)seeds_d, generation, mode, n_preserve, q, h->d_arch,
+                                                   shared ? h->d_arch + 24 : factions_d, shared ? 1 : 0, h->d_pools, h->d_pool_n,
+                                                   decks_d, factions_out_d);
   LAUNCH_CHECK();
   return 0;
 }
@@ -615,6 +773,9 @@ int sb_set_option(SbHandle* h, const char* key, int value) {
   if (!strcmp(key, "heur_wpc")) { h->heur_wpc = value; return 0; }
   if (!strcmp(key, "games_per_warp")) { h->gpw = value; return 0; }
   if (!strcmp(key, "ctas_per_sm")) { h->ctas_per_sm = value; return 0; }
+  if (!strcmp(key, "refill")) { h->refill = value; return 0; }
+  if (!strcmp(key, "refill_ctas")) { h->refill_ctas = value; return 0; }
+  if (!strcmp(key, "refill_grid")) { h->refill_grid = value; return 0; }
   return -1;
 }
 int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_first_d, const double* w_second_d,

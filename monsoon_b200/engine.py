@@ -77,6 +77,10 @@ class Engine:
     def launches(self):
         return int(self.lib.sb_launch_count(self.h))
 
+    def set_option(self, key, value):
+        """sb_set_option: tuning knobs of the rollout kernels (include/sb_b200.h)"""
+        self._check(self.lib.sb_set_option(self.h, key.encode(), int(value)), "sb_set_option(%s)" % key)
+
     def empty_states(self, n):
         return torch.empty((n, STATE_BYTES), dtype=torch.uint8, device=self.device)
 
@@ -99,6 +103,23 @@ class Engine:
         self._check(self.lib.sb_reset(self.h, n, self._p(seeds), self._p(decks), n_deck, shared, self._p(factions),
                                       self._p(states), self._stream()), "sb_reset")
         return states
+
+    def generate_decks(self, seeds, generation, mode, n_preserve=0, q=0.0, archetypes=None, arch_factions=None, factions=None):
+        """sb_generate_decks: per-game deck pairs of DeckEvolutionConfig.get_deck_configuration (utils.py:121-241).
+        Returns (decks u8[n,2,12], factions u8[n,2]) on the device, ready for reset()."""
+        seeds = torch.as_tensor(np.asarray(seeds, dtype=np.int64) if not torch.is_tensor(seeds) else seeds).to(self.device, torch.int64).contiguous()
+        n = seeds.numel()
+        arch = None if archetypes is None else np.ascontiguousarray(np.asarray(archetypes, dtype=np.uint8).reshape(24))
+        af = None if arch_factions is None else np.ascontiguousarray(np.asarray(arch_factions, dtype=np.uint8).reshape(2))
+        if factions is not None:
+            factions = torch.as_tensor(factions).to(self.device, torch.uint8).contiguous()
+            assert factions.shape == (n, 2)
+        decks = torch.empty((n, 2, 12), dtype=torch.uint8, device=self.device)
+        fout = torch.empty((n, 2), dtype=torch.uint8, device=self.device)
+        self._check(self.lib.sb_generate_decks(self.h, n, self._p(seeds), int(generation), int(mode), int(n_preserve), float(q),
+                                               None if arch is None else arch.ctypes.data, None if af is None else af.ctypes.data,
+                                               self._p(factions), self._p(decks), self._p(fout), self._stream()), "sb_generate_decks")
+        return decks, fout
 
     def legal_mask(self, states, out=None):
         n = states.shape[0]

@@ -188,6 +188,71 @@ def game_seed_array(base_seed, generation, i, j, k):
     return x.astype(np.int64)
 
 
+class DeckEvolutionConfig:
+    """utils.py:121-241: exploit -> explore -> balance schedule of the decks each game is dealt.
+
+    Archetypes are 12 card names ("UA07"), card-table indices or reference card objects.  The decks of a whole
+    batch are drawn on the device (`generate_batch` -> sb_generate_decks): game g uses its own counter-based
+    stream keyed by the game seed where the reference draws from the process-global `random` module.
+    """
+
+    def __init__(self, player1_archetype, player2_archetype, exploit_generations=30, explore_generations=30,
+                 max_random_ratio=0.5, balance_archetype_ratio=0.7):
+        from ._card_table import CARDS
+        index = {r["name"]: i for i, r in enumerate(CARDS)}
+
+        def ids(deck):
+            out = [c if isinstance(c, (int, np.integer)) else index[c if isinstance(c, str) else type(c).__name__] for c in deck]
+            if len(out) != 12:
+                raise NotImplementedError("archetypes of 12 cards only (the packed deck layout; utils.py pads/truncates)")
+            return [int(c) for c in out]
+
+        self.player1_archetype = ids(player1_archetype)
+        self.player2_archetype = ids(player2_archetype)
+        self.exploit_generations = exploit_generations
+        self.explore_generations = explore_generations
+        self.max_random_ratio = max_random_ratio
+        self.balance_archetype_ratio = balance_archetype_ratio
+        self.player1_faction = int(CARDS[self.player1_archetype[0]]["faction"])  # utils.py:152-153
+        self.player2_faction = int(CARDS[self.player2_archetype[0]]["faction"])
+        self._names = [r["name"] for r in CARDS]
+
+    def phase_parameters(self, generation):
+        """(mode, n_preserve, q) of sb_generate_decks for this generation (utils.py:155-218, :35-58)."""
+        if generation < self.exploit_generations:
+            return 0, 12, 0.0
+        if generation < self.exploit_generations + self.explore_generations:
+            progress = (generation - self.exploit_generations) / self.explore_generations
+            preserve_ratio = max(0.0, min(1.0, 1.0 - progress * self.max_random_ratio))
+            if preserve_ratio == 1.0:
+                return 1, 12, 0.0  # generate_random_deck returns original[:12]
+            return 1, (min(int(12 * preserve_ratio), 12) if preserve_ratio > 0.0 else 0), 0.0
+        return 2, 0, float(self.balance_archetype_ratio)
+
+    def generate_batch(self, engine, seeds, generation):
+        mode, n_preserve, q = self.phase_parameters(generation)
+        return engine.generate_decks(seeds, generation, mode, n_preserve, q, [self.player1_archetype, self.player2_archetype],
+                                     [self.player1_faction, self.player2_faction])
+
+    def get_deck_configuration(self, generation, seed=0, engine=None):
+        """One game's (player1_deck, player2_deck) as card names."""
+        decks, _f = self.generate_batch(engine or get_engine(), np.asarray([seed], dtype=np.int64), generation)
+        d = decks[0].cpu().numpy()
+        return [self._names[c] for c in d[0]], [self._names[c] for c in d[1]]
+
+    def get_phase_info(self, generation):  # utils.py:220-241
+        if generation < self.exploit_generations:
+            phase, random_ratio = "Exploit", 0.0
+        elif generation < self.exploit_generations + self.explore_generations:
+            phase = "Explore"
+            random_ratio = (generation - self.exploit_generations) / self.explore_generations * self.max_random_ratio
+        else:
+            phase, random_ratio = "Balance", 1.0 - self.balance_archetype_ratio
+        return {"phase": phase, "generation": generation, "random_ratio": random_ratio,
+                "exploit_complete": generation >= self.exploit_generations,
+                "explore_complete": generation >= self.exploit_generations + self.explore_generations}
+
+
 class FitnessEvaluator:
     """evo/fitness.py:18-259.  evaluate_population(population, generation) -> List[float] in [0, 1].
 
@@ -294,7 +359,12 @@ class FitnessEvaluator:
             seeds = game_seed_array(base_seed, generation, i_idx, j_idx, k)
             idx_first = torch.as_tensor(i_idx.astype(np.int32)).to(dev)
             idx_second = torch.as_tensor(j_idx.astype(np.int32)).to(dev)
-            states = eng.reset(torch.as_tensor(seeds).to(dev))
+            seeds_d = torch.as_tensor(seeds).to(dev)
+            if self.deck_config is not None:  # evo/fitness.py:136-141: generation-aware decks, drawn per game
+                decks, factions = self.deck_config.generate_batch(eng, seeds_d, generation)
+                states = eng.reset(seeds_d, decks, factions)
+            else:
+                states = eng.reset(seeds_d)
             result, _steps = eng.rollout_heuristic(states, w, w, idx_first, idx_second, max_steps=max_steps)
             eng.accumulate_fitness(result, idx_first, counts)
         if dist_on:
@@ -326,5 +396,5 @@ def play_game(adapter, agent1, agent2, max_turns=400):
     return adapter, turn_count
 
 
-__all__ = ["WeightVector", "StateFeatures", "StormboundAdapter", "HeuristicAgent", "FitnessEvaluator", "play_game",
+__all__ = ["WeightVector", "StateFeatures", "StormboundAdapter", "HeuristicAgent", "FitnessEvaluator", "DeckEvolutionConfig", "play_game",
            "game_seed", "mask_to_actions", "Game"]

@@ -425,3 +425,44 @@ def play_expert_game(seed, decks=None, factions=None, max_steps=400, record=True
                 digests=np.array(digests, dtype=np.uint64), states=states, err=err,
                 n_steps=step, done=bool(done), game=game)
 
+
+# ---------------------------------------------------------------- deck generation (utils.py:26-241)
+import random as _pyrandom
+
+
+class PhiloxPyRandom(_pyrandom.Random):
+    """Injected stand-in for the `random` module inside utils.py (sample / choices / random call shapes):
+    block = philox(counter=(draw, generation, 0xDEC4, 0), key=game seed).  random.sample itself is CPython's."""
+
+    def __init__(self, seed, generation):
+        super().__init__(0)
+        self._k = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self._gen = int(generation) & M32
+        self._draw = 0
+
+    def _block(self):
+        out = philox4x32_10(self._draw & M32, self._gen, 0xDEC4, 0, self._k & M32, self._k >> 32)
+        self._draw += 1
+        return out
+
+    def random(self):
+        w = self._block()
+        return ((w[0] >> 5) * 67108864 + (w[1] >> 6)) / 9007199254740992.0
+
+    def _randbelow(self, n):
+        return (self._block()[0] * n) >> 32
+
+
+def reference_decks(seed, generation, deck_config):
+    """(deck1, deck2) card indices that the UNMODIFIED DeckEvolutionConfig.get_deck_configuration(generation)
+    returns when utils.py draws from the injected stream of (seed, generation)."""
+    r = ref()
+    import utils
+    saved = utils.random
+    utils.random = PhiloxPyRandom(seed, generation)
+    try:
+        d1, d2 = deck_config.get_deck_configuration(generation)
+    finally:
+        utils.random = saved
+    return [[r.index[type(c).__name__] for c in d] for d in (d1, d2)]
+

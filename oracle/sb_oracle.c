@@ -1003,3 +1003,70 @@ int sbo_rollout_random(SbState *s, int max_steps, uint8_t *actions, uint64_t *di
   free(g);
   return k;
 }
+
+/* ------------------------------------------------------------------ deck generation (utils.py:26-241)
+ * generate_random_deck / DeckEvolutionConfig.get_deck_configuration with the injected stream
+ *   block = philox(counter=(draw, generation, 0xDEC4, 0), key=game seed)
+ * random.sample (CPython 3.12 Lib/random.py:359-452 call shape): pool method when n <= setsize, else the
+ * rejection-set method; _randbelow(n) = (w0*n)>>32, random() = 53-bit as everywhere else.
+ * mode 0 exploit (archetypes verbatim), 1 explore (n_preserve cards sampled from the archetype + random rest),
+ * 2 balance (two random() < q draws first, then archetype or a fully random deck per side),
+ * 3 fully random decks of the given factions.  decks: card ids [2][12]. */
+typedef struct { uint32_t lo, hi, gen, draw; } DeckRng;
+static uint32_t deck_w(DeckRng *r, uint32_t *w1) {
+  uint32_t w[4];
+  philox(r->draw++, r->gen, 0xDEC4u, 0, r->lo, r->hi, w);
+  if (w1) *w1 = w[1];
+  return w[0];
+}
+static int deck_below(DeckRng *r, int n) { return (int)(((uint64_t)deck_w(r, 0) * (uint64_t)n) >> 32); }
+static double deck_random(DeckRng *r) {
+  uint32_t w1, w0 = deck_w(r, &w1);
+  return ((double)(w0 >> 5) * 67108864.0 + (double)(w1 >> 6)) / 9007199254740992.0;
+}
+static void py_sample(DeckRng *r, const uint8_t *pop, int n, int k, uint8_t *out) {
+  int setsize = 21;
+  if (k > 5) { int x = 3 * k, p = 1; while (p < x) p *= 4; setsize += p; }  /* 4 ** ceil(log(3k, 4)) */
+  if (n <= setsize) {
+    uint8_t pool[128];
+    memcpy(pool, pop, (size_t)n);
+    for (int i = 0; i < k; i++) { int j = deck_below(r, n - i); out[i] = pool[j]; pool[j] = pool[n - i - 1]; }
+  } else {
+    uint8_t taken[128];
+    memset(taken, 0, sizeof taken);
+    for (int i = 0; i < k; i++) {
+      int j = deck_below(r, n);
+      while (taken[j]) j = deck_below(r, n);
+      taken[j] = 1; out[i] = pop[j];
+    }
+  }
+}
+static int faction_pool(int faction, uint8_t *pool) { /* dir(cards) order == card index order; own faction + NEUTRAL */
+  int n = 0;
+  for (int c = 1; c <= 112; c++) if (OCARDS[c].faction == faction || OCARDS[c].faction == 0) pool[n++] = (uint8_t)c;
+  return n;
+}
+static void random_deck(DeckRng *r, int faction, const uint8_t *original, int n_preserve, uint8_t *deck) {
+  uint8_t pool[128];
+  if (n_preserve >= 12) { memcpy(deck, original, 12); return; }  /* preserve_ratio == 1.0 */
+  if (n_preserve > 0) py_sample(r, original, 12, n_preserve, deck); else n_preserve = 0;
+  int n = faction_pool(faction, pool);
+  py_sample(r, pool, n, 12 - n_preserve, deck + n_preserve);
+}
+void sbo_generate_decks(uint64_t seed, uint32_t generation, int mode, int n_preserve, double q, const uint8_t *archetypes,
+                        const uint8_t *factions, uint8_t *decks) {
+  DeckRng r = {(uint32_t)seed, (uint32_t)(seed >> 32), generation, 0};
+  if (mode == 0) { memcpy(decks, archetypes, 24); return; }
+  if (mode == 1) { for (int o = 0; o < 2; o++) random_deck(&r, factions[o], archetypes + 12 * o, n_preserve, decks + 12 * o); return; }
+  if (mode == 2) {
+    int keep[2];
+    keep[0] = deck_random(&r) < q;
+    keep[1] = deck_random(&r) < q;
+    for (int o = 0; o < 2; o++) {
+      if (keep[o]) memcpy(decks + 12 * o, archetypes + 12 * o, 12);
+      else random_deck(&r, factions[o], archetypes + 12 * o, 0, decks + 12 * o);
+    }
+    return;
+  }
+  for (int o = 0; o < 2; o++) random_deck(&r, factions[o], archetypes, 0, decks + 12 * o);
+}

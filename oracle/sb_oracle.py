@@ -54,6 +54,8 @@ def lib():
         L.sbo_batch_heuristic.restype = ctypes.c_long
         L.sbo_expert_action.argtypes = [vp]
         L.sbo_expert_action.restype = ctypes.c_int
+        L.sbo_generate_decks.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp]
+        L.sbo_generate_decks.restype = None
         L.sbo_agent_pick.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]
         L.sbo_agent_pick.restype = ctypes.c_uint32
         assert L.sbo_state_bytes() == S
@@ -88,6 +90,15 @@ def step(st, action):
 def expert_action(st):
     """Stormbound.expert_action (games/stormbound.py:563-637); advances the random stream stored in st."""
     return int(lib().sbo_expert_action(_p(st)))
+
+
+def generate_decks(seed, generation, mode, n_preserve, q, archetypes, factions):
+    """DeckEvolutionConfig.get_deck_configuration (utils.py:121-241) for ONE game -> u8[2,12] card ids."""
+    arch = np.ascontiguousarray(np.asarray(archetypes, dtype=np.uint8).reshape(24))
+    fac = np.ascontiguousarray(np.asarray(factions, dtype=np.uint8).reshape(2))
+    out = np.zeros((2, 12), dtype=np.uint8)
+    lib().sbo_generate_decks(int(seed), int(generation), int(mode), int(n_preserve), float(q), _p(arch), _p(fac), _p(out))
+    return out
 
 
 def digest(st):

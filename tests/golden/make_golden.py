@@ -14,6 +14,9 @@ HeuristicAgent), then serialised with pack_reference.  Files:
                         excluded): decks, factions, steps, chain, final digest, outcome kind
   heuristic_decisions.npz  states sampled from reference HeuristicAgent-vs-HeuristicAgent games with the
                         reference's per-action scores, legal set and chosen action, plus whole-game results
+  deck_generation.npz   decks returned by the reference's DeckEvolutionConfig.get_deck_configuration /
+                        generate_random_deck (utils.py) drawing from the injected per-game stream: three schedules x
+                        every generation x 24 seeds, plus 400 fully random faction decks
   expert_tapes.npz      both seats play the reference's Stormbound.expert_action (it draws from the game's stream):
                         160 default-deck + 240 random-deck games, per-step actions and state digests
 """
@@ -130,10 +133,49 @@ def work_expert(seed):
             t["actions"], t["digests"], t["n_steps"], t["err"], int(t["done"]))
 
 
+DECK_SCHEDULES = (dict(), dict(exploit_generations=2, explore_generations=13, max_random_ratio=1.0, balance_archetype_ratio=0.4),
+                  dict(exploit_generations=0, explore_generations=7, max_random_ratio=0.8))
+
+
+def make_decks():
+    import ref_harness as h
+    from monsoon_b200.evo import DeckEvolutionConfig as Mirror
+    r = h.ref()
+    import utils
+    from enums import Faction
+    rows = []  # seed, generation, mode, n_preserve, q, factions[2], archetypes[24], decks[24]
+    a1, a2 = h.DEFAULT_DECKS
+    for kw in DECK_SCHEDULES:
+        ref_cfg = utils.DeckEvolutionConfig([getattr(r.cards, n)() for n in a1], [getattr(r.cards, n)() for n in a2], **kw)
+        mir = Mirror(a1, a2, **kw)
+        for gen in range(ref_cfg.exploit_generations + ref_cfg.explore_generations + 3):
+            assert ref_cfg.get_phase_info(gen) == mir.get_phase_info(gen)
+            mode, k, q = mir.phase_parameters(gen)
+            for j in range(24):
+                seed = j * 7919 + gen
+                d = h.reference_decks(seed, gen, ref_cfg)
+                rows.append((seed, gen, mode, k, q, [mir.player1_faction, mir.player2_faction],
+                             mir.player1_archetype + mir.player2_archetype, d[0] + d[1]))
+    for seed in range(400):
+        f = [1 + seed % 4, 1 + (seed // 4) % 4]
+        saved, utils.random = utils.random, h.PhiloxPyRandom(seed, 5)
+        try:
+            d = [[r.index[type(c).__name__] for c in utils.generate_random_deck(Faction(x))] for x in f]
+        finally:
+            utils.random = saved
+        rows.append((seed, 5, 3, 0, 0.0, f, [0] * 24, d[0] + d[1]))
+    np.savez_compressed(os.path.join(HERE, "deck_generation.npz"),
+                        seeds=np.array([x[0] for x in rows], dtype=np.uint64), generation=np.array([x[1] for x in rows], dtype=np.uint32),
+                        mode=np.array([x[2] for x in rows], dtype=np.uint8), n_preserve=np.array([x[3] for x in rows], dtype=np.uint8),
+                        q=np.array([x[4] for x in rows], dtype=np.float64), factions=np.array([x[5] for x in rows], dtype=np.uint8),
+                        archetypes=np.array([x[6] for x in rows], dtype=np.uint8), decks=np.array([x[7] for x in rows], dtype=np.uint8))
+    print("deck_generation.npz", len(rows))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--procs", type=int, default=os.cpu_count())
-    ap.add_argument("--only", default="tapes,chain,rand,heur,expert")
+    ap.add_argument("--only", default="tapes,chain,rand,heur,expert,decks")
     ap.add_argument("--n-chain", type=int, default=10000)
     ap.add_argument("--n-rand", type=int, default=3000)
     ap.add_argument("--n-heur", type=int, default=24)
@@ -182,6 +224,8 @@ def main():
                             weights=np.stack([s[1] for s in samples]), masks=np.stack([s[2] for s in samples]),
                             scores=np.stack([s[3] for s in samples]), chosen=np.array([s[4] for s in samples], dtype=np.uint8))
         print("heuristic_decisions.npz games", len(res), "samples", len(samples))
+    if "decks" in only:
+        make_decks()
     if "expert" in only:
         res = pool.map(work_expert, list(range(160)) + list(range(200000, 200240)), chunksize=4)
         np.savez_compressed(os.path.join(HERE, "expert_tapes.npz"),

@@ -78,3 +78,47 @@ def test_fitness_evaluator_matches_oracle(engine, oracle):
                 want[i] += 1.0 if r == 0 else 0.5 if r < 0 else 0.0
     assert np.allclose(fit, want / (3 * 2)) and len(fit) == 4 and all(0 <= x <= 1 for x in fit)
     assert len(ev.hall_of_fame) == 4 and ev.get_stats()["total_games"] == 24
+
+
+def test_fitness_evaluator_with_deck_schedule(engine, oracle):
+    """evo/fitness.py:136-141: with a deck_config every game is dealt its own generation-aware decks."""
+    from monsoon_b200.evo import DeckEvolutionConfig, FitnessEvaluator, WeightVector, game_seed
+    from monsoon_b200.engine import DEFAULT_DECKS
+    cfg = DeckEvolutionConfig(DEFAULT_DECKS[0], DEFAULT_DECKS[1], exploit_generations=1, explore_generations=4,
+                              max_random_ratio=1.0, balance_archetype_ratio=0.5)
+    np.random.seed(9)
+    pop = [WeightVector(10) for _ in range(3)]
+    arch, fac = [cfg.player1_archetype, cfg.player2_archetype], [cfg.player1_faction, cfg.player2_faction]
+    for generation in (0, 3, 7):  # exploit, explore, balance
+        ev = FitnessEvaluator(Cfg(), deck_config=cfg, engine=engine)
+        fit = ev.evaluate_population(pop, generation=generation)
+        mode, keep, q = cfg.phase_parameters(generation)
+        want, flagged = np.zeros(3), 0
+        for i in range(3):
+            for j in range(3):
+                if i == j:
+                    continue
+                for k in range(2):
+                    seed = game_seed(11, generation, i, j, k)
+                    d = oracle.generate_decks(seed, generation, mode, keep, q, arch, fac)
+                    st = oracle.new_game(seed, d[0], d[1], fac[0], fac[1])
+                    r, _ = oracle.play_heuristic(st, pop[i].weights, pop[j].weights, 400)
+                    flagged += r == -2
+                    want[i] += 1.0 if r == 0 else 0.5 if r == -1 else 0.0
+        assert np.allclose(fit, want / (2 * 2)), (generation, fit, want, flagged)
+
+
+def test_deck_generation_matches_oracle_at_scale(engine, oracle):
+    seeds = (np.arange(6000, dtype=np.int64) * 2654435761) % (1 << 40)
+    arch = np.arange(1, 25, dtype=np.uint8).reshape(2, 12)
+    for mode, keep, q in ((1, 3, 0.0), (1, 9, 0.0), (2, 0, 0.35), (3, 0, 0.0)):
+        fac = np.stack([1 + seeds % 4, 1 + (seeds // 4) % 4], axis=1).astype(np.uint8)
+        if mode == 3:
+            decks, _ = engine.generate_decks(seeds, 17, 3, factions=fac)
+        else:
+            decks, _ = engine.generate_decks(seeds, 17, mode, keep, q, arch, [2, 4])
+        decks = decks.cpu().numpy()
+        for i in range(0, 6000, 7):
+            want = oracle.generate_decks(int(seeds[i]), 17, mode, keep, q, arch, fac[i] if mode == 3 else [2, 4])
+            assert np.array_equal(decks[i], want), (mode, i)
+

@@ -30,6 +30,30 @@ def test_10k_default_games_rollout_kernel(engine):
     assert (host[~ok][:, 18] != 0).all()  # games where the reference raised are flagged
 
 
+def test_10k_default_games_lane_refill(engine):
+    """Same fixture through the persistent-lane schedule (finished lanes take the next game from a counter):
+    1,024 lanes play 10,000 games, results must not depend on which lane played which game."""
+    z = load("default_chain_10k.npz")
+    ok = z["err"] == 0
+    seeds = torch.from_numpy(z["seeds"].astype(np.int64)).to(engine.device)
+    try:
+        for bs, grid in ((128, 8), (1024, 2)):
+            engine.set_option("refill", 1)
+            engine.set_option("block_sync", bs)
+            engine.set_option("refill_grid", grid)
+            engine.set_option("games_per_warp", 32)
+            st = engine.reset(seeds)
+            chain = torch.zeros(len(seeds), dtype=torch.int64, device=engine.device)
+            steps = engine.rollout_random(st, 400, chain=chain)
+            steps, chain = steps.cpu().numpy(), chain.cpu().numpy().view(np.uint64)
+            assert np.array_equal(steps[ok], z["steps"][ok]), bs
+            assert np.array_equal(chain[ok], z["chain"][ok]), bs
+            assert (st.cpu().numpy()[~ok][:, 18] != 0).all()
+    finally:
+        for k, v in (("refill", -1), ("block_sync", -1), ("refill_grid", 0), ("games_per_warp", 0)):
+            engine.set_option(k, v)
+
+
 def test_random_deck_games_rollout_kernel(engine):
     z = load("randdeck_chain.npz")
     dev = engine.device
@@ -45,6 +69,28 @@ def test_random_deck_games_rollout_kernel(engine):
     raised = (z["err"] != 0) & ~unsupported
     assert (host[raised][:, 18] != 0).all() and np.array_equal(steps[raised], z["steps"][raised] + 1)
     assert unsupported.sum() <= len(unsupported) * 3 // 200
+
+
+def test_deck_generation_kernel(engine):
+    """sb_generate_decks against the decks the reference's utils.py produced (every schedule phase, both
+    random.sample call shapes), batched by identical parameters."""
+    z = load("deck_generation.npz")
+    key = np.stack([z["generation"], z["mode"], z["n_preserve"], (z["q"] * 1000).astype(np.uint32)], axis=1)
+    done = 0
+    for u in np.unique(key, axis=0):
+        sel = np.nonzero((key == u).all(axis=1))[0]
+        mode = int(u[1])
+        if mode == 3:
+            decks, fout = engine.generate_decks(z["seeds"][sel].astype(np.int64), int(u[0]), 3, factions=z["factions"][sel])
+        else:
+            i0 = sel[0]
+            assert (z["archetypes"][sel] == z["archetypes"][i0]).all()
+            decks, fout = engine.generate_decks(z["seeds"][sel].astype(np.int64), int(u[0]), mode, int(u[2]), float(z["q"][i0]),
+                                                z["archetypes"][i0], z["factions"][i0])
+        assert np.array_equal(decks.cpu().numpy().reshape(len(sel), 24), z["decks"][sel]), u
+        assert np.array_equal(fout.cpu().numpy(), z["factions"][sel])
+        done += len(sel)
+    assert done == len(z["seeds"])
 
 
 def fnv1a64_rows(rows):

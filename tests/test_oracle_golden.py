@@ -131,6 +131,15 @@ def test_expert_games(oracle):
     assert tolerated <= len(z["seeds"]) * 3 // 200, tolerated
 
 
+def test_deck_generation(oracle):
+    """utils.py generate_random_deck / DeckEvolutionConfig decks recorded from the reference (injected stream)."""
+    z = load("deck_generation.npz")
+    for i in range(len(z["seeds"])):
+        got = oracle.generate_decks(int(z["seeds"][i]), int(z["generation"][i]), int(z["mode"][i]), int(z["n_preserve"][i]),
+                                    float(z["q"][i]), z["archetypes"][i], z["factions"][i])
+        assert np.array_equal(got.reshape(24), z["decks"][i]), i
+
+
 def test_heuristic_scores_and_choices(oracle):
     """Float action scores within 1e-5 relative of the reference's; identical choices where the top-two gap
     exceeds that tolerance (BASELINE north star)."""
