@@ -82,6 +82,25 @@ int sb_generate_decks(SbHandle *h, int n, const uint64_t *seeds_d, uint32_t gene
                       const uint8_t *archetypes, const uint8_t *arch_factions, const uint8_t *factions_d, uint8_t *decks_d,
                       uint8_t *factions_out_d, void *stream);
 
+/* ---- (mu + lambda) evolution-strategy operators on a device-resident population.
+ * weights / sigmas: f64 [rows][n_features] row-major, n_features <= 64, mu <= 4096.  Row r draws from
+ * philox(counter=(draw, r, tag, generation), key=seed) with the reference's call shapes; exp/log use correctly
+ * rounded basic operations only, so results are bit-identical to oracle/sb_oracle_es.c.
+ *
+ * sb_es_offspring: Population.generate_offspring (evo/population.py:75-90) + WeightVector.mutate
+ * (evo/weights.py:20-40): child c = mutate(copy(parent randint(0, mu))) written to row mu + c; parents_d nullable i32[lambda].
+ * sb_es_select: the top-mu part of Population.select_from_combined (evo/population.py:99-107): fitness descending,
+ * ties in input order; order_d nullable i32[mu] = source row of each survivor.
+ * sb_es_reset_sigmas: evo/population.py:128-139.  sb_es_inject_diversity: evo/population.py:146-170; chosen_d
+ * nullable i32[max(1, mu/2)].  The caller evaluates the two trigger conditions from the survivors' statistics. */
+int sb_es_offspring(SbHandle *h, uint64_t seed, uint32_t generation, int mu, int lambda, int n_features, double tau, double tau_prime,
+                    double min_sigma, double *w_d, double *s_d, int32_t *parents_d, void *stream);
+int sb_es_select(SbHandle *h, int total, int mu, int n_features, const double *fitness_d, const double *w_d, const double *s_d,
+                 double *w_out_d, double *s_out_d, double *fit_out_d, int32_t *order_d, void *stream);
+int sb_es_reset_sigmas(SbHandle *h, uint64_t seed, uint32_t generation, int mu, int n_features, double initial_sigma, double *s_d, void *stream);
+int sb_es_inject_diversity(SbHandle *h, uint64_t seed, uint32_t generation, int mu, int n_features, double tau, double tau_prime,
+                           double min_sigma, double initial_sigma, double *w_d, double *s_d, int32_t *chosen_d, void *stream);
+
 /* Stormbound.expert_action (games/stormbound.py:563-637) for n games: the scripted opponent behind
  * Game.expert_agent (games/stormbound.py:201-209).  It draws its choices from the GAME's stream, so each
  * state's draw counter (and err byte, for the reference's choice([]) / max([]) exceptions) is updated in

@@ -33,6 +33,11 @@ SIGNATURES = {
     "sb_features": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "sb_select_action": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp]),
     "sb_generate_decks": (_int, [_vp, _int, _vp, ctypes.c_uint32, _int, _int, ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_es_offspring": (_int, [_vp, ctypes.c_uint64, ctypes.c_uint32, _int, _int, _int, ctypes.c_double, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _vp]),
+    "sb_es_select": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_es_reset_sigmas": (_int, [_vp, ctypes.c_uint64, ctypes.c_uint32, _int, _int, ctypes.c_double, _vp, _vp]),
+    "sb_es_inject_diversity": (_int, [_vp, ctypes.c_uint64, ctypes.c_uint32, _int, _int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                      ctypes.c_double, _vp, _vp, _vp, _vp]),
     "sb_expert_action": (_int, [_vp, _int, _vp, _vp, _vp]),
     "sb_rollout_random": (_int, [_vp, _int, _vp, _int, _vp, _vp, _vp]),
     "sb_rollout_heuristic": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),

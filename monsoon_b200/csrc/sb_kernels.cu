@@ -12,6 +12,7 @@
 //                      warp arg-max by shuffles) -- evo/heuristic_agent.py:53-80
 //   k_rollout_heuristic  one warp per game, whole game in one launch, base state staged in shared memory
 //   k_accumulate_fitness win/draw/loss counts per individual (evo/fitness.py:95,160-166)
+//   k_es_*             evolution-strategy operators on the resident population (sb_es.cuh; evo/weights.py, evo/population.py)
 // State is AoS [n][512 B]; every thread (or warp) moves its record with 128-bit loads/stores; the card
 // table (130 x 24 B) is staged in shared memory once per CTA.
 #include <cuda_runtime.h>
@@ -21,6 +22,7 @@
 #include "../../include/sb_b200.h"
 #include "sb_effects.cuh"
 #include "sb_state_io.cuh"
+#include "sb_es.cuh"
 
 #define SB_ABI_VERSION 1
 #define TPB_GAME 64      // threads per CTA for thread-per-game kernels
@@ -716,6 +718,44 @@ int sb_generate_decks(SbHandle* h, int n, const uint64_t* seeds_d, uint32_t gene
   k_generate_decks<<<grid_for(n, 128), 128, 0, st>>>(n, (const unsigned long long*)seeds_d, generation, mode, n_preserve, q, h->d_arch,
                                                    shared ? h->d_arch + 24 : factions_d, shared ? 1 : 0, h->d_pools, h->d_pool_n,
                                                    decks_d, factions_out_d);
+  LAUNCH_CHECK();
+  return 0;
+}
+static int es_args_ok(SbHandle* h, int mu, int nf, const char* what) {
+  if (mu <= 0 || mu > ES_MAX_MU || nf <= 0 || nf > ES_MAX_FEATURES) {
+    snprintf(h->err, sizeof h->err, "%s: mu must be 1..%d and n_features 1..%d", what, ES_MAX_MU, ES_MAX_FEATURES);
+    return 0;
+  }
+  return 1;
+}
+int sb_es_offspring(SbHandle* h, uint64_t seed, uint32_t generation, int mu, int lambda, int n_features, double tau, double tau_prime,
+                    double min_sigma, double* w_d, double* s_d, int32_t* parents_d, void* stream) {
+  if (!es_args_ok(h, mu, n_features, "sb_es_offspring")) return -1;
+  if (lambda <= 0) return 0;
+  k_es_offspring<<<grid_for(lambda, 128), 128, 0, (cudaStream_t)stream>>>(seed, generation, mu, lambda, n_features, tau, tau_prime, min_sigma,
+                                                                         w_d, s_d, parents_d);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_es_select(SbHandle* h, int total, int mu, int n_features, const double* fitness_d, const double* w_d, const double* s_d,
+                 double* w_out_d, double* s_out_d, double* fit_out_d, int32_t* order_d, void* stream) {
+  if (!es_args_ok(h, mu, n_features, "sb_es_select")) return -1;
+  if (total < mu) { snprintf(h->err, sizeof h->err, "sb_es_select: total < mu"); return -1; }
+  k_es_select<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(total, mu, n_features, fitness_d, w_d, s_d, w_out_d, s_out_d, fit_out_d, order_d);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_es_reset_sigmas(SbHandle* h, uint64_t seed, uint32_t generation, int mu, int n_features, double initial_sigma, double* s_d, void* stream) {
+  if (!es_args_ok(h, mu, n_features, "sb_es_reset_sigmas")) return -1;
+  k_es_reset_sigmas<<<grid_for(mu, 128), 128, 0, (cudaStream_t)stream>>>(seed, generation, mu, n_features, initial_sigma, s_d);
+  LAUNCH_CHECK();
+  return 0;
+}
+int sb_es_inject_diversity(SbHandle* h, uint64_t seed, uint32_t generation, int mu, int n_features, double tau, double tau_prime,
+                           double min_sigma, double initial_sigma, double* w_d, double* s_d, int32_t* chosen_d, void* stream) {
+  if (!es_args_ok(h, mu, n_features, "sb_es_inject_diversity")) return -1;
+  k_es_inject_diversity<<<1, 256, 0, (cudaStream_t)stream>>>(seed, generation, mu, n_features, tau, tau_prime, min_sigma, initial_sigma, w_d, s_d,
+                                                             chosen_d);
   LAUNCH_CHECK();
   return 0;
 }

@@ -121,6 +121,34 @@ class Engine:
                                                self._p(factions), self._p(decks), self._p(fout), self._stream()), "sb_generate_decks")
         return decks, fout
 
+    # ---- evolution-strategy operators on a resident population (include/sb_b200.h, sb_es_*)
+    def es_offspring(self, seed, generation, mu, lam, tau, tau_prime, min_sigma, w, s, parents=None):
+        assert w.shape == s.shape and w.shape[0] >= mu + lam and w.dtype == torch.float64 and w.is_contiguous() and s.is_contiguous()
+        self._check(self.lib.sb_es_offspring(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(generation), mu, lam, w.shape[1], float(tau),
+                                             float(tau_prime), float(min_sigma), self._p(w), self._p(s), self._p(parents), self._stream()),
+                    "sb_es_offspring")
+
+    def es_select(self, mu, fitness, w, s, want_order=False):
+        total, nf = w.shape
+        fitness = torch.as_tensor(fitness, dtype=torch.float64).to(self.device).contiguous()
+        assert fitness.numel() == total
+        wo = torch.empty((mu, nf), dtype=torch.float64, device=self.device)
+        so = torch.empty_like(wo)
+        fo = torch.empty(mu, dtype=torch.float64, device=self.device)
+        order = torch.empty(mu, dtype=torch.int32, device=self.device) if want_order else None
+        self._check(self.lib.sb_es_select(self.h, total, mu, nf, self._p(fitness), self._p(w), self._p(s), self._p(wo), self._p(so),
+                                          self._p(fo), self._p(order), self._stream()), "sb_es_select")
+        return wo, so, fo, order
+
+    def es_reset_sigmas(self, seed, generation, initial_sigma, s):
+        self._check(self.lib.sb_es_reset_sigmas(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(generation), s.shape[0], s.shape[1],
+                                                float(initial_sigma), self._p(s), self._stream()), "sb_es_reset_sigmas")
+
+    def es_inject_diversity(self, seed, generation, tau, tau_prime, min_sigma, initial_sigma, w, s, chosen=None):
+        self._check(self.lib.sb_es_inject_diversity(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF, int(generation), w.shape[0], w.shape[1], float(tau),
+                                                    float(tau_prime), float(min_sigma), float(initial_sigma), self._p(w), self._p(s),
+                                                    self._p(chosen), self._stream()), "sb_es_inject_diversity")
+
     def legal_mask(self, states, out=None):
         n = states.shape[0]
         masks = out if out is not None else torch.empty((n, MASK_WORDS), dtype=torch.int32, device=self.device)

@@ -48,6 +48,19 @@ class WeightVector:
     def get_weights(self):
         return self.weights.copy()
 
+    def get_sigmas(self):
+        return self.sigmas.copy()
+
+    def set_weights(self, weights):
+        if len(weights) != self.size:
+            raise ValueError("Weight array size %d doesn't match expected size %d" % (len(weights), self.size))
+        self.weights = np.clip(weights, 0, 1)
+
+    def set_sigmas(self, sigmas):
+        if len(sigmas) != self.size:
+            raise ValueError("Sigma array size %d doesn't match expected size %d" % (len(sigmas), self.size))
+        self.sigmas = np.maximum(sigmas, 1e-10)
+
     def distance_to(self, other):
         return np.linalg.norm(self.weights - other.weights)
 

@@ -466,3 +466,133 @@ def reference_decks(seed, generation, deck_config):
         utils.random = saved
     return [[r.index[type(c).__name__] for c in d] for d in (d1, d2)]
 
+
+# ---------------------------------------------------------------- evolution-strategy operators (evo/weights.py, evo/population.py)
+import math as _math
+import struct as _struct
+
+
+def det_log(x):
+    """sbo_det_log restated in Python floats (IEEE double, no fused operations): identical bits."""
+    u = _struct.unpack("<Q", _struct.pack("<d", x))[0]
+    e = ((u >> 52) & 0x7FF) - 1022
+    m = _struct.unpack("<d", _struct.pack("<Q", (u & 0x000FFFFFFFFFFFFF) | 0x3FE0000000000000))[0]
+    if m < 0.70710678118654752440:
+        m = m * 2.0
+        e -= 1
+    z = (m - 1.0) / (m + 1.0)
+    z2 = z * z
+    p = 1.0 / 27.0
+    for k in range(25, 0, -2):
+        p = p * z2 + 1.0 / float(k)
+    return float(e) * 0.693147180559945309417232 + 2.0 * z * p
+
+
+class EsStream:
+    """Stand-in for `np.random` inside evo/weights.py and evo/population.py: the call shapes of generate_offspring
+    (randint, normal(), normal(size), normal(0, sigmas)), of the sigma reset (uniform(lo, hi, n)) and of the
+    diversity injection (choice(n, k, replace=False), then 9 normal calls per chosen row) mapped onto per-row
+    counter streams philox(counter=(draw, row, tag, generation), key=seed)."""
+
+    def __init__(self, seed):
+        self.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        self.generation = 0
+        self.tag, self.row, self.draw = 0xE5, 0, 0
+        self.children = 0
+        self.resets = 0
+        self.queue, self.normal_calls = [], 0
+
+    def begin(self, generation):
+        self.generation = int(generation)
+        self.children = self.resets = 0
+        self.queue, self.normal_calls = [], 0
+
+    def _block(self):
+        out = philox4x32_10(self.draw & M32, self.row & M32, self.tag, self.generation & M32, self.seed & M32, self.seed >> 32)
+        self.draw += 1
+        return out
+
+    @staticmethod
+    def _u53(a, b):
+        return ((a >> 5) * 67108864 + (b >> 6)) / 9007199254740992.0
+
+    def _gauss(self):
+        while True:
+            w = self._block()
+            u = 2.0 * self._u53(w[0], w[1]) - 1.0
+            v = 2.0 * self._u53(w[2], w[3]) - 1.0
+            s = u * u + v * v
+            if s >= 1.0 or s == 0.0:
+                continue
+            return u * _math.sqrt(-2.0 * det_log(s) / s)
+
+    def randint(self, low, high):
+        self.tag, self.row, self.draw = 0xE5, self.children, 0
+        self.children += 1
+        return low + ((self._block()[0] * (high - low)) >> 32)
+
+    def normal(self, loc=0.0, scale=1.0, size=None):
+        if self.queue:  # diversity injection: 3 mutate calls x 3 normal calls per chosen row
+            if self.normal_calls % 9 == 0:
+                self.tag, self.row, self.draw = 0xE7, self.queue[self.normal_calls // 9], 0
+            self.normal_calls += 1
+        if size is None and np.ndim(scale) == 0:
+            return loc + scale * self._gauss()
+        n = size if size is not None else len(scale)
+        z = np.array([self._gauss() for _ in range(n)])
+        return loc + np.asarray(scale, dtype=np.float64) * z
+
+    def uniform(self, low, high, size):
+        if low == 0 and high == 1:  # WeightVector.__init__ inside parent.copy(): overwritten at once, draws nothing here
+            return np.zeros(size)
+        self.tag, self.row, self.draw = 0xE6, self.resets, 0
+        self.resets += 1
+        out = np.empty(size)
+        for i in range(size):
+            w = self._block()
+            out[i] = low + (high - low) * self._u53(w[0], w[1])
+        return out
+
+    def choice(self, n, k, replace=False):
+        assert not replace
+        self.tag, self.row, self.draw = 0xE7, 0xFFFFFFFF, 0
+        perm = list(range(n))
+        for i in range(n - 1, 0, -1):
+            j = (self._block()[0] * (i + 1)) >> 32
+            perm[i], perm[j] = perm[j], perm[i]
+        self.queue, self.normal_calls = perm[:k], 0
+        return np.array(perm[:k])
+
+    def seed_(self, *_a):
+        pass
+
+
+class NumpyWithStream:
+    """`np` as seen by the reference's evo modules: numpy, except `.random`."""
+
+    def __init__(self, stream):
+        self.random = stream
+
+    def __getattr__(self, name):
+        return getattr(np, name)
+
+
+def reference_population(config_kwargs, seed):
+    """(population object, stream): the reference's Population with evo.weights / evo.population drawing from an
+    EsStream.  Initial individuals are set by the caller (set_weights / set_sigmas)."""
+    ref()
+    import contextlib
+    import io
+    import evo.population as rp
+    import evo.weights as rw
+    from evo.config import EvolutionaryConfig
+    stream = EsStream(seed)
+    shim = NumpyWithStream(stream)
+    rp.np = shim
+    rw.np = shim
+    cfg = EvolutionaryConfig(**config_kwargs)
+    cfg.seed = None  # Population.__init__ would call np.random.seed
+    with contextlib.redirect_stdout(io.StringIO()):
+        pop = rp.Population(cfg)
+    return pop, stream, rw.WeightVector
+

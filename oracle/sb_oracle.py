@@ -17,7 +17,7 @@ _lib = None
 
 
 def build(force=False):
-    srcs = ["sb_oracle.c", "sb_oracle_effects.c", "sb_oracle_agent.c", "sb_oracle.h", "sb_card_table.inc",
+    srcs = ["sb_oracle.c", "sb_oracle_effects.c", "sb_oracle_agent.c", "sb_oracle_es.c", "sb_oracle.h", "sb_card_table.inc",
             "sb_card_ids.h", os.path.join("..", "include", "sb_state.h")]
     newest = max(os.path.getmtime(os.path.join(HERE, s)) for s in srcs)
     if force or not os.path.exists(SO) or os.path.getmtime(SO) < newest:
@@ -56,6 +56,17 @@ def lib():
         L.sbo_expert_action.restype = ctypes.c_int
         L.sbo_generate_decks.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_double, vp, vp, vp]
         L.sbo_generate_decks.restype = None
+        dbl, u64, u32, i32 = ctypes.c_double, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+        L.sbo_det_log.argtypes = [dbl]
+        L.sbo_det_log.restype = dbl
+        L.sbo_det_exp.argtypes = [dbl]
+        L.sbo_det_exp.restype = dbl
+        L.sbo_es_offspring.argtypes = [u64, u32, i32, i32, i32, dbl, dbl, dbl, vp, vp, vp]
+        L.sbo_es_select.argtypes = [i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
+        L.sbo_es_reset_sigmas.argtypes = [u64, u32, i32, i32, dbl, vp]
+        L.sbo_es_inject_diversity.argtypes = [u64, u32, i32, i32, dbl, dbl, dbl, dbl, vp, vp, vp]
+        for f in (L.sbo_es_offspring, L.sbo_es_select, L.sbo_es_reset_sigmas, L.sbo_es_inject_diversity):
+            f.restype = None
         L.sbo_agent_pick.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32]
         L.sbo_agent_pick.restype = ctypes.c_uint32
         assert L.sbo_state_bytes() == S
@@ -99,6 +110,33 @@ def generate_decks(seed, generation, mode, n_preserve, q, archetypes, factions):
     out = np.zeros((2, 12), dtype=np.uint8)
     lib().sbo_generate_decks(int(seed), int(generation), int(mode), int(n_preserve), float(q), _p(arch), _p(fac), _p(out))
     return out
+
+
+# ---- evolution-strategy operators (sb_oracle_es.c); w, s: float64 [rows, nf] C-contiguous, modified in place
+def es_offspring(seed, generation, mu, lam, tau, tau_prime, min_sigma, w, s):
+    parents = np.zeros(lam, dtype=np.int32)
+    lib().sbo_es_offspring(int(seed), int(generation), mu, lam, w.shape[1], tau, tau_prime, min_sigma, _p(w), _p(s), _p(parents))
+    return parents
+
+
+def es_select(mu, fitness, w, s):
+    total, nf = w.shape
+    fitness = np.ascontiguousarray(fitness, dtype=np.float64)
+    wo, so, fo = np.zeros((mu, nf)), np.zeros((mu, nf)), np.zeros(mu)
+    order = np.zeros(mu, dtype=np.int32)
+    lib().sbo_es_select(total, mu, nf, _p(fitness), _p(w), _p(s), _p(wo), _p(so), _p(fo), _p(order))
+    return wo, so, fo, order
+
+
+def es_reset_sigmas(seed, generation, initial_sigma, s):
+    lib().sbo_es_reset_sigmas(int(seed), int(generation), s.shape[0], s.shape[1], initial_sigma, _p(s))
+
+
+def es_inject_diversity(seed, generation, tau, tau_prime, min_sigma, initial_sigma, w, s):
+    chosen = np.zeros(max(1, w.shape[0] // 2), dtype=np.int32)
+    lib().sbo_es_inject_diversity(int(seed), int(generation), w.shape[0], w.shape[1], tau, tau_prime, min_sigma, initial_sigma,
+                                  _p(w), _p(s), _p(chosen))
+    return chosen
 
 
 def digest(st):

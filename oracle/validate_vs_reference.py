@@ -153,3 +153,77 @@ def check_expert_seed(seed, decks=None, factions=None, max_steps=400):
             print("seed", seed, "reference raised (kind %d) at step" % tape["err"], tape["n_steps"], "oracle did not")
             return False, tape["n_steps"], tape
     return True, tape["n_steps"], tape
+
+
+def es_reference_generation(pop, stream, fitness_fn):
+    """One reference generation after the first: offspring, then select_from_combined on given fitness values."""
+    import contextlib
+    import io
+    stream.begin(pop.generation)
+    with contextlib.redirect_stdout(io.StringIO()):
+        offspring = pop.generate_offspring()
+        snapshot = (np.array([c.weights for c in offspring]), np.array([c.sigmas for c in offspring]))  # select mutates survivors in place
+        everyone = pop.get_parents() + offspring
+        fitness = fitness_fn(len(everyone))
+        stream.begin(pop.generation + 1)
+        pop.select_from_combined(everyone, list(fitness))
+    return snapshot, fitness
+
+
+def es_oracle_generation(seed, generation, cfg, w, s, fitness_fn):
+    """The same generation with the oracle's operators; mirrors the conditions of evo/population.py:92-176."""
+    mu, lam = cfg["mu"], cfg["lambda_"]
+    W = np.concatenate([w, np.zeros((lam, w.shape[1]))])
+    S = np.concatenate([s, np.zeros((lam, w.shape[1]))])
+    parents = o.es_offspring(seed, generation, mu, lam, cfg["tau"], cfg["tau_prime"], cfg["min_sigma"], W, S)
+    fitness = fitness_fn(mu + lam)
+    w2, s2, f2, order = o.es_select(mu, fitness, W, S)
+    events = []
+    if np.mean(s2) < cfg["min_sigma"] * 10:
+        o.es_reset_sigmas(seed, generation + 1, cfg["initial_sigma"], s2)
+        events.append("reset")
+    if np.std(f2) < 1e-3 and np.std(f2) == 0.0 and len(set(f2.tolist())) == 1:
+        o.es_inject_diversity(seed, generation + 1, cfg["tau"], cfg["tau_prime"], cfg["min_sigma"], cfg["initial_sigma"], w2, s2)
+        events.append("inject")
+    return W[mu:], S[mu:], parents, w2, s2, f2, order, events
+
+
+def check_es(seed=5, generations=6, mu=12, lam=20, scenario="normal"):
+    cfg = dict(mu=mu, lambda_=lam, tau=0.1, tau_prime=0.01, min_sigma=1e-5, initial_sigma=0.1)
+    pop, stream, WV = h.reference_population(cfg, seed)
+    rs = np.random.RandomState(seed)
+    w = rs.uniform(0, 1, (mu, 10))
+    s = rs.uniform(0.05, 0.2, (mu, 10)) if scenario != "reset" else rs.uniform(1e-5, 5e-5, (mu, 10))
+    pop.individuals = []
+    for i in range(mu):
+        v = WV(10)
+        v.set_weights(w[i].copy())
+        v.set_sigmas(s[i].copy())
+        pop.individuals.append(v)
+    pop.fitness_scores = [0.0] * mu
+    pop.generation = 1
+    worst = 0.0
+    seen = set()
+    for g in range(generations):
+        frs = np.random.RandomState(1000 * seed + g)
+        if scenario == "inject" and g % 2 == 1:
+            fit_fn = lambda n: np.full(n, 0.5)
+        else:
+            vals = np.round(frs.uniform(0, 1, mu + lam), 1)  # one decimal: many ties -> exercises the stable order
+            fit_fn = lambda n, vals=vals: vals[:n]
+        gen = pop.generation
+        offspring, fitness = es_reference_generation(pop, stream, fit_fn)
+        ow, os_, parents, w2, s2, f2, order, events = es_oracle_generation(seed, gen, cfg, w, s, fit_fn)
+        seen.update(events)
+        rw_, rsg = offspring
+        worst = max(worst, np.max(np.abs(rw_ - ow)), np.max(np.abs(rsg - os_) / rsg))
+        nw = np.array([c.weights for c in pop.individuals])
+        ns = np.array([c.sigmas for c in pop.individuals])
+        if not np.array_equal(np.array(pop.fitness_scores), f2):
+            print("ES fitness order mismatch at generation", gen)
+            return False
+        worst = max(worst, np.max(np.abs(nw - w2)), np.max(np.abs(ns - s2) / ns))
+        w, s = nw.copy(), ns.copy()  # continue from the reference's state
+    print("check_es", scenario, "generations", generations, "events", sorted(seen), "max deviation %.3g" % worst)
+    return worst < 1e-12
+

@@ -17,6 +17,11 @@ HeuristicAgent), then serialised with pack_reference.  Files:
   deck_generation.npz   decks returned by the reference's DeckEvolutionConfig.get_deck_configuration /
                         generate_random_deck (utils.py) drawing from the injected per-game stream: three schedules x
                         every generation x 24 seeds, plus 400 fully random faction decks
+  es_operators.npz      the reference's Population.generate_offspring / select_from_combined and
+                        WeightVector.mutate driven with the per-row streams (oracle/ref_harness.EsStream): three
+                        scenarios (plain, sigma reset, diversity injection) x 4 generations
+  ref_population.pkl    a checkpoint written by the reference's Population.save_population
+  ref_training_log.csv  two rows written by the reference's EvolutionEngine._save_generation_log
   expert_tapes.npz      both seats play the reference's Stormbound.expert_action (it draws from the game's stream):
                         160 default-deck + 240 random-deck games, per-step actions and state digests
 """
@@ -172,10 +177,65 @@ def make_decks():
     print("deck_generation.npz", len(rows))
 
 
+ES_CFG = dict(mu=12, lambda_=20, tau=0.1, tau_prime=0.01, min_sigma=1e-5, initial_sigma=0.1)
+
+
+def make_es():
+    import contextlib
+    import io
+    import ref_harness as h
+    import validate_vs_reference as v
+    out = {}
+    for si, scenario in enumerate(("normal", "reset", "inject")):
+        seed = 21 + si
+        pop, stream, WV = h.reference_population(ES_CFG, seed)
+        rs = np.random.RandomState(seed)
+        mu, lam = ES_CFG["mu"], ES_CFG["lambda_"]
+        w = rs.uniform(0, 1, (mu, 10))
+        s = rs.uniform(0.05, 0.2, (mu, 10)) if scenario != "reset" else rs.uniform(1e-5, 5e-5, (mu, 10))
+        pop.individuals = []
+        for i in range(mu):
+            x = WV(10)
+            x.set_weights(w[i].copy())
+            x.set_sigmas(s[i].copy())
+            pop.individuals.append(x)
+        pop.fitness_scores, pop.generation = [0.0] * mu, 1
+        out["%s_seed" % scenario] = np.int64(seed)
+        out["%s_w0" % scenario], out["%s_s0" % scenario] = w, s
+        fits, ow, os_, sw, ss, sf = [], [], [], [], [], []
+        for g in range(4):
+            vals = np.full(mu + lam, 0.5) if (scenario == "inject" and g % 2 == 1) else np.round(np.random.RandomState(100 * seed + g).uniform(0, 1, mu + lam), 1)
+            (cw, cs), _f = v.es_reference_generation(pop, stream, lambda n, vals=vals: vals[:n])
+            fits.append(vals)
+            ow.append(cw)
+            os_.append(cs)
+            sw.append(np.array([c.weights for c in pop.individuals]))
+            ss.append(np.array([c.sigmas for c in pop.individuals]))
+            sf.append(np.array(pop.fitness_scores))
+        for k, a in (("fitness", fits), ("off_w", ow), ("off_s", os_), ("sur_w", sw), ("sur_s", ss), ("sur_f", sf)):
+            out["%s_%s" % (scenario, k)] = np.stack(a)
+        if scenario == "normal":  # f4: files written by the reference itself
+            with contextlib.redirect_stdout(io.StringIO()):
+                pop.save_population(os.path.join(HERE, "ref_population.pkl"))
+                import evo.evolution as re_
+                eng = re_.EvolutionEngine.__new__(re_.EvolutionEngine)
+                eng.results_dir = HERE
+                log = os.path.join(HERE, "training_log.csv")
+                if os.path.exists(log):
+                    os.remove(log)
+                st = pop.get_population_stats()
+                eng._save_generation_log(st, {"games_per_second": 1234.56}, 7.891)
+                eng._save_generation_log(dict(st, generation=st["generation"] + 1, best_fitness=0.75), {"games_per_second": 99.0}, 0.004)
+                os.replace(log, os.path.join(HERE, "ref_training_log.csv"))
+            out["log_stats"] = np.array([st[k] for k in ("generation", "best_fitness", "mean_fitness", "std_fitness", "diversity", "avg_mutation_strength")])
+    np.savez_compressed(os.path.join(HERE, "es_operators.npz"), **out)
+    print("es_operators.npz", len(out), "arrays; ref_population.pkl; ref_training_log.csv")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--procs", type=int, default=os.cpu_count())
-    ap.add_argument("--only", default="tapes,chain,rand,heur,expert,decks")
+    ap.add_argument("--only", default="tapes,chain,rand,heur,expert,decks,es")
     ap.add_argument("--n-chain", type=int, default=10000)
     ap.add_argument("--n-rand", type=int, default=3000)
     ap.add_argument("--n-heur", type=int, default=24)
@@ -226,6 +286,8 @@ def main():
         print("heuristic_decisions.npz games", len(res), "samples", len(samples))
     if "decks" in only:
         make_decks()
+    if "es" in only:
+        make_es()
     if "expert" in only:
         res = pool.map(work_expert, list(range(160)) + list(range(200000, 200240)), chunksize=4)
         np.savez_compressed(os.path.join(HERE, "expert_tapes.npz"),

@@ -2,6 +2,7 @@
 reference-faithful evaluator, hall of fame, and the N>1 reduction path over gloo (world_size 2)."""
 import os
 import socket
+import subprocess
 import sys
 
 import numpy as np
@@ -129,3 +130,83 @@ def test_two_rank_gloo_matches_single_rank():
         p.join(60)
     for _rank, fit, counts in got:
         assert fit == want and counts == single.last_counts.tolist()
+
+
+# ---------------------------------------------------------------- f4: checkpoint / log formats
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_reads_reference_checkpoint():
+    """A pickle written by the reference's Population.save_population (evo/population.py:281-296)."""
+    from monsoon_b200.training import EvolutionaryConfig, load_checkpoint
+    from monsoon_b200.evo import WeightVector
+    d = load_checkpoint(os.path.join(GOLDEN, "ref_population.pkl"))
+    z = np.load(os.path.join(GOLDEN, "es_operators.npz"))
+    assert d["generation"] == 5 and len(d["individuals"]) == 12 and isinstance(d["config"], EvolutionaryConfig)
+    assert all(isinstance(v, WeightVector) for v in d["individuals"])
+    assert np.array_equal(np.array([v.weights for v in d["individuals"]]), z["normal_sur_w"][-1])
+    assert np.array_equal(np.array([v.sigmas for v in d["individuals"]]), z["normal_sur_s"][-1])
+    assert d["fitness_scores"] == z["normal_sur_f"][-1].tolist() and d["config"].mu == 12 and d["config"].lambda_ == 20
+
+
+def test_checkpoint_round_trip_and_reference_class_paths(tmp_path):
+    import pickletools
+    from monsoon_b200.training import EvolutionaryConfig, dump_checkpoint, load_checkpoint
+    from monsoon_b200.evo import WeightVector
+    np.random.seed(3)
+    data = {"generation": 9, "individuals": [WeightVector(10) for _ in range(4)], "fitness_scores": [0.5, 0.25, 0.125, 0.0],
+            "config": EvolutionaryConfig(mu=4, lambda_=4, seed=1)}
+    path = tmp_path / "ours.pkl"
+    dump_checkpoint(data, str(path))
+    ops = [(op.name, arg) for op, arg, _pos in pickletools.genops(path.read_bytes())]
+    names = {arg for name, arg in ops if name in ("SHORT_BINUNICODE", "BINUNICODE")}
+    assert {"evo.weights", "WeightVector", "evo.config", "EvolutionaryConfig"} <= names  # what the reference will import
+    assert not any("monsoon_b200" in str(arg) for _n, arg in ops)
+    back = load_checkpoint(str(path))
+    assert back["generation"] == 9 and back["fitness_scores"] == data["fitness_scores"] and back["config"] == data["config"]
+    for a, b in zip(back["individuals"], data["individuals"]):
+        assert np.array_equal(a.weights, b.weights) and np.array_equal(a.sigmas, b.sigmas) and a.size == b.size
+    assert "evo" not in sys.modules or not hasattr(sys.modules["evo"], "__path__") or sys.modules["evo"].__path__ != []
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/evo"), reason="needs the reference checkout (build container only)")
+def test_reference_loads_our_checkpoint(tmp_path):
+    """The other direction, where the reference is present: its own Population.load_population reads our file."""
+    from monsoon_b200.training import EvolutionaryConfig, dump_checkpoint
+    from monsoon_b200.evo import WeightVector
+    np.random.seed(4)
+    vecs = [WeightVector(10) for _ in range(3)]
+    path = tmp_path / "ours.pkl"
+    dump_checkpoint({"generation": 2, "individuals": vecs, "fitness_scores": [0.9, 0.8, 0.7], "config": EvolutionaryConfig(mu=3, lambda_=3)}, str(path))
+    code = ("import sys, pickle, numpy as np; sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r);"
+            "from evo.population import Population; from evo.config import EvolutionaryConfig; from evo.weights import WeightVector;"
+            "p = Population(EvolutionaryConfig()); p.load_population(%r);"
+            "assert p.generation == 2 and p.config.mu == 3 and type(p.individuals[0]) is WeightVector;"
+            "p.individuals[0].mutate(0.1, 0.01, 1e-5); print(repr(p.individuals[1].weights.tolist()))"
+            % (os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "refshim"), str(path)))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/root/reference")
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert eval(out.stdout.strip().splitlines()[-1]) == vecs[1].weights.tolist()
+
+
+def test_training_log_rows_match_reference_format(tmp_path):
+    from monsoon_b200.training import append_generation_log
+    z = np.load(os.path.join(GOLDEN, "es_operators.npz"))
+    keys = ("generation", "best_fitness", "mean_fitness", "std_fitness", "diversity", "avg_mutation_strength")
+    st = dict(zip(keys, z["log_stats"].tolist()))
+    st["generation"] = int(st["generation"])
+    log = tmp_path / "training_log.csv"
+    append_generation_log(str(log), st, {"games_per_second": 1234.56}, 7.891)
+    append_generation_log(str(log), dict(st, generation=st["generation"] + 1, best_fitness=0.75), {"games_per_second": 99.0}, 0.004)
+    assert log.read_text() == open(os.path.join(GOLDEN, "ref_training_log.csv")).read()
+
+
+def test_config_mirror_matches_reference_defaults():
+    from monsoon_b200.training import EvolutionaryConfig, load_checkpoint
+    ref_cfg = load_checkpoint(os.path.join(GOLDEN, "ref_population.pkl"))["config"]
+    ours = EvolutionaryConfig(mu=12, lambda_=20, tau=0.1, tau_prime=0.01, min_sigma=1e-5, initial_sigma=0.1)
+    assert vars(ref_cfg).keys() == vars(ours).keys()  # the reference's dataclass fields, all of them
+    assert vars(ref_cfg) == vars(ours)
+    with pytest.raises(ValueError):
+        EvolutionaryConfig(mu=0)
+

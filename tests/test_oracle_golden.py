@@ -140,6 +140,40 @@ def test_deck_generation(oracle):
         assert np.array_equal(got.reshape(24), z["decks"][i]), i
 
 
+ES_CFG = dict(mu=12, lambda_=20, tau=0.1, tau_prime=0.01, min_sigma=1e-5, initial_sigma=0.1)
+
+
+def es_generation(oracle, seed, generation, w, s, fitness, cfg=ES_CFG):
+    """One (mu + lambda) generation with the oracle's operators and the conditions of evo/population.py:92-176."""
+    mu, lam = cfg["mu"], cfg["lambda_"]
+    W = np.concatenate([w, np.zeros((lam, w.shape[1]))])
+    S = np.concatenate([s, np.zeros((lam, w.shape[1]))])
+    oracle.es_offspring(seed, generation, mu, lam, cfg["tau"], cfg["tau_prime"], cfg["min_sigma"], W, S)
+    w2, s2, f2, _order = oracle.es_select(mu, fitness, W, S)
+    if np.mean(s2) < cfg["min_sigma"] * 10:
+        oracle.es_reset_sigmas(seed, generation + 1, cfg["initial_sigma"], s2)
+    if np.std(f2) == 0.0 and len(set(f2.tolist())) == 1:
+        oracle.es_inject_diversity(seed, generation + 1, cfg["tau"], cfg["tau_prime"], cfg["min_sigma"], cfg["initial_sigma"], w2, s2)
+    return W[mu:], S[mu:], w2, s2, f2
+
+
+def test_es_operators(oracle):
+    """generate_offspring / mutate / select_from_combined recorded from the reference (per-row streams injected):
+    selection order exact, weights and sigmas within 1e-12 (the reference uses numpy's exp)."""
+    z = load("es_operators.npz")
+    for scenario in ("normal", "reset", "inject"):
+        seed = int(z[scenario + "_seed"])
+        w, s = z[scenario + "_w0"].copy(), z[scenario + "_s0"].copy()
+        for g in range(z[scenario + "_fitness"].shape[0]):
+            ow, os_, w2, s2, f2 = es_generation(oracle, seed, 1 + g, w, s, z[scenario + "_fitness"][g])
+            assert np.allclose(ow, z[scenario + "_off_w"][g], rtol=0, atol=1e-12), (scenario, g)
+            assert np.allclose(os_, z[scenario + "_off_s"][g], rtol=1e-12, atol=0), (scenario, g)
+            assert np.array_equal(f2, z[scenario + "_sur_f"][g]), (scenario, g)
+            assert np.allclose(w2, z[scenario + "_sur_w"][g], rtol=0, atol=1e-12), (scenario, g)
+            assert np.allclose(s2, z[scenario + "_sur_s"][g], rtol=1e-12, atol=0), (scenario, g)
+            w, s = z[scenario + "_sur_w"][g].copy(), z[scenario + "_sur_s"][g].copy()
+
+
 def test_heuristic_scores_and_choices(oracle):
     """Float action scores within 1e-5 relative of the reference's; identical choices where the top-two gap
     exceeds that tolerance (BASELINE north star)."""
