@@ -49,18 +49,33 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.sm, self.mx, self.reasons, self.stop_flag, self.how = index, [], [], set(), False, "nvml"
 
+    def prepare(self):
+        """NVML handle set up BEFORE the timed region, so that even a few-millisecond region gets its samples."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self._mx = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self._nv = None
+
+    def sample_once(self):
+        """One NVML sample; also called from the main thread right after the launches, while the GPU is busy."""
+        if getattr(self, "_nv", None) is None:
+            return
+        self.sm.append(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM))
+        self.mx.append(self._mx)
+        r = self._nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for name, bit in self.BITS.items():
+            if r & bit:
+                self.reasons.add(name)
+
     def _nvml(self):
-        import pynvml
-        pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        if getattr(self, "_nv", None) is None:
+            raise RuntimeError("nvml unavailable")
         while not self.stop_flag:
-            self.sm.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
-            self.mx.append(mx)
-            r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
-            for name, bit in self.BITS.items():
-                if r & bit:
-                    self.reasons.add(name)
+            self.sample_once()
             time.sleep(0.005)
 
     def _smi(self):
@@ -187,14 +202,18 @@ def main():
     for k in range(warmup):
         one_pass(k, False)
     torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.prepare()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank)
+    launches0 = eng.launches
     if rank == 0:
         sampler.start()
-    launches0 = eng.launches
     events = [one_pass(warmup + k, True) for k in range(args.steps)]
+    if rank == 0:
+        sampler.sample_once()  # launches are asynchronous: the GPU is inside the timed work here
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

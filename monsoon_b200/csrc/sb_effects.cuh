@@ -18,6 +18,7 @@ SBD_FI int choice_pt(G& g, const i8* l, int n) {
 // list.sort(key=lambda t: (k1(t), random.random()), reverse=desc): one random() per element in list order,
 // then a stable sort (cards/b002.py:20, b008.py:24, b009.py:20, b104.py:19, s101.py:21)
 SBD_NI void keyed_sort(G& g, i8* pts, const i16* k1, int n, bool desc) {
+  G_LOCAL(g);
   double r[22];
   i16 k[22];
   #pragma unroll 1
@@ -36,6 +37,7 @@ SBD_NI void keyed_sort(G& g, i8* pts, const i16* k1, int n, bool desc) {
   }
 }
 SBD_NI int count_types_friendly(G& g) {  // cards/up02.py:13-19, up03.py:14-20
+  G_LOCAL(g);
   Target t = mkT(TK_UNIT, TS_FRIENDLY);
   i8 pts[22];
   int n = get_targets(g, CUR(g), t, PT_NONE, pts);
@@ -52,6 +54,7 @@ SBD_FI int empty_of(const G& g, const i8* in, int n, i8* out) {
 }
 // "frontmost enemy" family: get_targets -> keyed sort on y desc -> take `take`
 SBD_NI int frontmost(G& g, const Target& t, i8* pts) {
+  G_LOCAL(g);
   int n = get_targets(g, CUR(g), t, PT_NONE, pts);
   if (n > 0) {
     i16 ky[22];
@@ -64,6 +67,7 @@ SBD_NI int frontmost(G& g, const Target& t, i8* pts) {
 
 // ---- Temple of Time memories (cards/b005.py:13,24-33): a forest of deep copies, see Mem in sb_engine.cuh
 SBD_NI int mem_push_entity(G& g, int temple, int parent, int pos, const Ent& s) {
+  G_LOCAL(g);
   if (g.n_mem >= NMEM) { GERR(g, SB_ERR_OVERFLOW); return -1; }
   Mem& m = g.mem[g.n_mem];
   m.b005 = (i8)temple; m.parent = (i8)parent; m.pos = (u8)pos; m.card = s.card; m.fl = s.fl & (EF_OWNER | EF_STRUCT | EF_FIXED);
@@ -74,6 +78,7 @@ SBD_NI int mem_push_entity(G& g, int temple, int parent, int pos, const Ent& s) 
 }
 // deep copy of the subtree rooted at mem[src] under new_parent (iterative: parents precede children in the array)
 SBD_NI int mem_copy_subtree(G& g, int src, int new_parent, int limit) {
+  G_LOCAL(g);
   i8 map[NMEM];
   #pragma unroll 1
   for (int q = 0; q < NMEM; q++) map[q] = -1;
@@ -95,6 +100,7 @@ SBD_NI int mem_copy_subtree(G& g, int src, int new_parent, int limit) {
   return root;
 }
 SBD_NI void mem_delete_temple(G& g, int temple) {  // self.ability_remembered = []
+  G_LOCAL(g);
   u8 keep[NMEM], nidx[NMEM];
   int w = 0;
   #pragma unroll 1
@@ -113,6 +119,7 @@ SBD_NI void mem_delete_temple(G& g, int temple) {  // self.ability_remembered = 
 }
 
 SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
+  G_LOCAL(g);
   Ent& e = g.e[id];
   const DCard& cd = CARD(g, e.card);
   const i8* p = cd.p;
@@ -731,6 +738,7 @@ SBD_NI void effect(G& g, int id, int pos_pt, int has_source) {
 }
 
 SBD_NI void spell_effect(G& g, int card, int caster, int pos_pt) {
+  G_LOCAL(g);
   const i8* p = CARD(g, card).p;
   i8 pts[22];
   int n, tid;

@@ -108,6 +108,13 @@ struct G {
 };
 
 #define GERR(g, code) do { if (!(g).err) (g).err = (code); } while (0)
+// Every G is a thread-private local of its kernel.  Telling the compiler so at the top of the out-of-line functions
+// turns the generic 64-bit loads/stores through `G&` into local-space ones (no per-access descriptor moves).
+#ifdef __CUDA_ARCH__
+#define G_LOCAL(g) __builtin_assume(__isLocal(&(g)))
+#else
+#define G_LOCAL(g) ((void)0)
+#endif
 
 SBD_FI int PTX(int pt) { return pt >= 20 ? -1 : (pt & 3); }
 SBD_FI int PTY(int pt) { return pt == PT_BASE_REMOTE ? -1 : pt == PT_BASE_LOCAL ? 5 : (pt >> 2); }
@@ -134,6 +141,7 @@ SBD_FI void philox(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1, u32& o0, u32&
 // rollout kernels are instruction-fetch bound, so code size matters more than a call)
 SBD_NI double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 SBD_NI int rng_below(G& g, int n) {
+  G_LOCAL(g);
   if (n <= 0) { GERR(g, SB_ERR_EMPTY_CHOICE); return 0; }
   u32 w0, w1;
   philox(g.draw, g.turn, 0, 0, g.seed_lo, g.seed_hi, w0, w1);
@@ -141,6 +149,7 @@ SBD_NI int rng_below(G& g, int n) {
   return (int)__umulhi(w0, (u32)n);
 }
 SBD_NI double rng_random(G& g) {
+  G_LOCAL(g);
   u32 w0, w1;
   philox(g.draw, g.turn, 0, 0, g.seed_lo, g.seed_hi, w0, w1);
   g.draw++;
@@ -188,6 +197,7 @@ SBD_FI int next_tile(u32& m, bool ascending) {
   return t;
 }
 SBD_NI void calc_front_line(G& g, int order) {  // board.py:78-92
+  G_LOCAL(g);
   const bool local = order == g.local_order;
   int fl = local ? 4 : 0;
   const u32 m = g.occ & (order ? g.own1 : ~g.own1);  // this side's entities: first (local) / last (remote) occupied row
@@ -210,7 +220,7 @@ SBD_FI Target card_target(const DCard& c) {
   return t;
 }
 // the rare filters of board.py:170-179 (side and kind are already decided by the bitmasks of the caller)
-SBD_NI bool ent_matches_filters(const G& g, const Ent& e, const Target& t) {
+SBD_FI bool ent_matches_filters(const G& g, const Ent& e, const Target& t) {
   if (t.has_limit && e.strength > t.limit) return false;
   if (ent_struct(e)) return true;  // structures only honour strength_limit (board.py:179)
   u16 types = CARD(g, e.card).types;
@@ -232,6 +242,7 @@ SBD_NI bool ent_matches_filters(const G& g, const Ent& e, const Target& t) {
 // region = bitmask over tiles (bit t) that a tile must belong to; 0xFFFFF = whole board.
 // base_passes: base points survive the region filter when include_base (board.py:215,262,276,294).
 SBD_NI int get_targets_region(const G& g, int pov, const Target& t, int exclude_pt, u32 region, bool base_passes, i8* out) {
+  G_LOCAL(g);
   int n = 0;
   bool pov_local = (pov == g.local_order);
   // side and kind are decided by bitmask algebra (own1 = tiles whose entity belongs to order 1, strc =
@@ -320,6 +331,7 @@ SBD_FI void sort_pts_by_y(i8* a, int n, bool desc) {  // stable insertion sort o
 }
 // board.py:206-234.  toward_enemy: front tiles; else behind tiles.  t == nullptr: the plain tile list.
 SBD_NI int column_tiles(const G& g, int x, int y, int pov, const Target* t, bool front, i8* out) {
+  G_LOCAL(g);
   bool pov_local = (pov == g.local_order);
   bool up = (pov_local == front);  // decreasing y
   int n = 0;
@@ -355,6 +367,7 @@ SBD_FI int within_front_line_tiles(const G& g, int order, i8* out) {  // player.
 
 // ---------------------------------------------------------------- entities
 SBD_NI int new_ent(G& g, int card, int owner, int strength) {
+  G_LOCAL(g);
   if (g.n_ent >= MAXE) { GERR(g, SB_ERR_OVERFLOW); return MAXE - 1; }
   int id = g.n_ent++;
   Ent& e = g.e[id];
@@ -368,6 +381,7 @@ SBD_NI int new_ent(G& g, int card, int owner, int strength) {
   return id;
 }
 SBD_NI int spawn_token_unit(G& g, int owner, int pt, int strength, int type) {  // board.py:298-311
+  G_LOCAL(g);
   int id = new_ent(g, SBC_TOKEN_UNIT0 + type, owner, strength);
   set_xy(g, PTX(pt), PTY(pt), id);
   calc_front_line(g, owner);
@@ -387,11 +401,13 @@ SBD_FI void push_trigger(G& g, int id, int has_source) {
   g.trig[g.n_trig++] = (u8)(id | (has_source ? 0x80 : 0));
 }
 SBD_NI void pop_trigger(G& g) {
+  G_LOCAL(g);
   if (g.n_trig == 0 || g.resolving) return;
   u8 t = g.trig[--g.n_trig];
   ability(g, t & 0x7F, PT_NONE, t >> 7);
 }
 SBD_NI void ability(G& g, int id, int pos_pt, int has_source) {
+  G_LOCAL(g);
   if (!(CARD(g, g.e[id].card).flags & DCF_ABILITY)) return;  // un-overridden Card.activate_ability: no wrapper
   if (g.depth > MAXDEPTH) { GERR(g, SB_ERR_DEPTH); return; }
   g.depth++;
@@ -402,6 +418,7 @@ SBD_NI void ability(G& g, int id, int pos_pt, int has_source) {
   g.depth--;
 }
 SBD_NI void spell_ability(G& g, int card, int caster, int pos_pt) {
+  G_LOCAL(g);
   if (g.depth > MAXDEPTH) { GERR(g, SB_ERR_DEPTH); return; }
   g.depth++;
   g.resolving = 1;
@@ -426,6 +443,7 @@ SBD_FI void v_heal(G& g, int id, int amount) { g.e[id].strength = (i16)(g.e[id].
 // ---------------------------------------------------------------- damage (unit.py:205-231, structure.py:52-69, player.py:83-88)
 SBD_FI int player_damage(G& g, int order, int amount) { g.pl[order].base = (i16)(g.pl[order].base - amount); return amount; }
 SBD_NI void destroy(G& g, int id, int has_source) {
+  G_LOCAL(g);
   Ent& e = g.e[id];
   clear_at(g, e);  // by (possibly stale) position, like board.set(self.position, None) (Q21)
   e.dmg = e.strength;
@@ -436,6 +454,7 @@ SBD_NI void destroy(G& g, int id, int has_source) {
   calc_front_line(g, opponent_of(g, g.current_order));
 }
 SBD_NI int deal_damage(G& g, int id, int amount, int pending, int has_source) {
+  G_LOCAL(g);
   Ent& e = g.e[id];
   if (e.strength - amount < 0) amount = e.strength;
   e.dmg = (i16)amount;
@@ -445,6 +464,7 @@ SBD_NI int deal_damage(G& g, int id, int amount, int pending, int has_source) {
   return amount;
 }
 SBD_NI int deal_damage_pt(G& g, int pt, int amount, int has_source) {  // board.at(point).deal_damage(...)
+  G_LOCAL(g);
   if (pt == PT_BASE_LOCAL) return player_damage(g, g.local_order, amount);
   if (pt == PT_BASE_REMOTE) return player_damage(g, 1 - g.local_order, amount);
   int id = at_pt(g, pt);
@@ -455,6 +475,7 @@ SBD_NI int deal_damage_pt(G& g, int pt, int amount, int has_source) {  // board.
 // ---------------------------------------------------------------- movement (unit.py:66-203, 277-382)
 SBD_FI u8 enc_xy(int x, int y) { return (u8)((y + 1) * 4 + x); }
 SBD_NI void set_path(G& g, int id, int on_play, int extra_movement) {  // unit.py:78-122
+  G_LOCAL(g);
   Ent& e = g.e[id];
   u8 dest[MAXPATH];
   int nd = 0;
@@ -497,6 +518,7 @@ SBD_NI void set_path(G& g, int id, int on_play, int extra_movement) {  // unit.p
 }
 
 SBD_NI void unit_move(G& g, int id) {  // unit.py:124-203
+  G_LOCAL(g);
   Ent& e = g.e[id];
   if (g.depth > MAXDEPTH) { GERR(g, SB_ERR_DEPTH); return; }
   g.depth++;
@@ -557,6 +579,7 @@ SBD_NI void unit_move(G& g, int id) {  // unit.py:124-203
   g.depth--;
 }
 SBD_NI void unit_play(G& g, int id, int x, int y) {  // unit.py:66-76
+  G_LOCAL(g);
   g.e[id].fl |= EF_RPLAY;
   set_xy(g, x, y, id);
   set_path(g, id, 1, 0);
@@ -565,11 +588,13 @@ SBD_NI void unit_play(G& g, int id, int x, int y) {  // unit.py:66-76
   g.e[id].fl &= ~EF_RPLAY;
 }
 SBD_NI void struct_play(G& g, int id, int x, int y) {  // structure.py:45-50
+  G_LOCAL(g);
   set_xy(g, x, y, id);
   if (CARD(g, g.e[id].card).trigger == TR_ON_PLAY) ability(g, id, PT_NONE, 1);
 }
 SBD_FI void gain_speed(G& g, int id, int amount) { set_path(g, id, (g.e[id].fl & EF_RPLAY) != 0, amount); }  // unit.py:277-280
 SBD_NI void v_command(G& g, int id) {  // unit.py:282-289
+  G_LOCAL(g);
   u8 cache = g.e[id].fl & EF_FIXED;
   g.e[id].fl |= EF_FIXED;
   set_path(g, id, 0, 0);
@@ -577,6 +602,7 @@ SBD_NI void v_command(G& g, int id) {  // unit.py:282-289
   g.e[id].fl = (u8)((g.e[id].fl & ~EF_FIXED) | cache);
 }
 SBD_NI void v_convert(G& g, int id) {  // unit.py:291-293
+  G_LOCAL(g);
   Ent& e = g.e[id];
   int o = opponent_of(g, ent_owner(e));
   e.fl = (u8)((e.fl & ~EF_OWNER) | (o ? EF_OWNER : 0));
@@ -587,6 +613,7 @@ SBD_NI void v_convert(G& g, int id) {  // unit.py:291-293
   set_path(g, id, (e.fl & EF_RPLAY) != 0, 0);
 }
 SBD_NI void v_push(G& g, int id, int fx, int fy) {  // unit.py:318-339
+  G_LOCAL(g);
   Ent& e = g.e[id];
   int dx = 0, dy = 0;
   if (fy < e.y) dy = 1; else if (fy > e.y) dy = -1; else if (fx < e.x) dx = 1; else if (fx > e.x) dx = -1;
@@ -604,6 +631,7 @@ SBD_NI void v_push(G& g, int id, int fx, int fy) {  // unit.py:318-339
   if (p.front_line > e.y) p.front_line = (i8)(e.y > 1 ? e.y : 1);
 }
 SBD_NI void v_force_attack(G& g, int id, int tx, int ty) {  // unit.py:341-371
+  G_LOCAL(g);
   Ent& e = g.e[id];
   if ((tx != e.x && ty != e.y) || at_xy(g, tx, ty) < 0) return;
   u8 dest[MAXPATH];
@@ -625,6 +653,7 @@ SBD_NI void v_force_attack(G& g, int id, int tx, int ty) {  // unit.py:341-371
   }
 }
 SBD_NI void v_teleport(G& g, int id, int dx, int dy) {  // unit.py:373-382
+  G_LOCAL(g);
   Ent& e = g.e[id];
   if (at_xy(g, dx, dy) < 0) {
     clear_at(g, e);
@@ -640,7 +669,7 @@ SBD_NI void v_teleport(G& g, int id, int dx, int dy) {  // unit.py:373-382
 // card_id, player, position (unit.py:25-26, structure.py:18-19); Spell: uuid (card.py:22-23).  A board
 // instance of B305 (SB_CF_OBJ) has a Point position, a pristine card None: comparing the two evaluates
 // Point.__eq__(None) -> AttributeError (point.py:7).
-SBD_NI int first_equal(G& g, const CardRec* l, int n, int idx) {
+SBD_FI int first_equal(G& g, const CardRec* l, int n, int idx) {
   const CardRec t = l[idx];
   if (CARD(g, t.card).kind == KIND_SPELL) return idx;
   #pragma unroll 1
@@ -653,30 +682,48 @@ SBD_NI int first_equal(G& g, const CardRec* l, int n, int idx) {
   return idx;
 }
 SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + numpy choice(p=) semantics
+  G_LOCAL(g);
   Ply& p = g.pl[order];
   #pragma unroll 1
   for (int k = 0; k < amount; k++) {
     int n = p.n_deck;
     if (n <= 0) { GERR(g, SB_ERR_EMPTY_CHOICE); return; }
+    double wv[DECK_W];
     double sum = 0.0;
     #pragma unroll 1
-    for (int i = 0; i < n; i++) sum = __dadd_rn(sum, __ldg(&g.wt[p.deck[i].wn]));
-    double cdf[DECK_W];
-    double acc = 0.0;
-    #pragma unroll 1
-    for (int i = 0; i < n; i++) { acc = __dadd_rn(acc, ddiv(__ldg(&g.wt[p.deck[i].wn]), sum)); cdf[i] = acc; }
-    double last = cdf[n - 1];
-    double u = rng_random(g);
-    // idx = #{i : fl(cdf_i / last) <= u} (searchsorted side='right' on the normalised cdf).  Rounding is
-    // monotone, so the quotient only has to be formed when cdf_i is within 1e-15 (> 2^-50) of u*last;
-    // everywhere else the comparison is decided without the FP64 division.
-    const double t = __dmul_rn(u, last);
-    const double t_lo = __dmul_rn(t, 0.999999999999999), t_hi = __dmul_rn(t, 1.000000000000001);
+    for (int i = 0; i < n; i++) { wv[i] = __ldg(&g.wt[p.deck[i].wn]); sum = __dadd_rn(sum, wv[i]); }
+    const double u = rng_random(g);
+    // numpy: p_i = fl(w_i / sum), cdf = cumsum(p), cdf /= cdf[-1], idx = searchsorted(cdf, u, side='right')
+    //      = #{i : fl(cdf_i / last) <= u}.
+    // Fast path: one division.  a_i = sum_j w_j * (1/sum) differs from the exactly rounded fl(cdf_i / last) by less
+    // than 1e-14 (n <= 20 terms, each a few ulp of a value <= 1; last = 1 +- n ulp), so the comparison with u is
+    // already decided whenever |a_i - u| > 1e-13.  Only a draw that lands closer than that to a boundary (about one
+    // in 1e12) takes the exact path below, which forms every quotient like numpy does.
+    const double inv = ddiv(1.0, sum);
     int idx = 0;
-    #pragma unroll 1
-    for (int i = 0; i < n; i++) {
-      const double c = cdf[i];
-      if (c < t_lo || (c <= t_hi && ddiv(c, last) <= u)) idx++;
+    bool close_call = false;
+    {
+      double acc = 0.0;
+      #pragma unroll 1
+      for (int i = 0; i < n; i++) {
+        acc += wv[i] * inv;
+        const double d = acc - u;
+        idx += d < -1e-13;
+        close_call |= (d >= -1e-13) & (d <= 1e-13);
+      }
+    }
+#ifdef SB_FORCE_EXACT_DRAW  // test builds: always take the exact path
+    close_call = true;
+#endif
+    if (close_call) {
+      double cdf[DECK_W];
+      double acc = 0.0;
+      #pragma unroll 1
+      for (int i = 0; i < n; i++) { acc = __dadd_rn(acc, ddiv(wv[i], sum)); cdf[i] = acc; }
+      const double last = cdf[n - 1];
+      idx = 0;
+      #pragma unroll 1
+      for (int i = 0; i < n; i++) idx += ddiv(cdf[i], last) <= u;
     }
     if (idx > n - 1) idx = n - 1;
     CardRec c = p.deck[idx];
@@ -692,6 +739,7 @@ SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + num
 }
 SBD_FI void player_fill_hand(G& g, int order) { player_draw(g, order, 4 - g.pl[order].n_hand); }
 SBD_NI void player_discard(G& g, int order, int index) {  // player.py:57-66
+  G_LOCAL(g);
   Ply& p = g.pl[order];
   #pragma unroll 1
   for (int i = 0; i < p.n_deck; i++) { if (p.deck[i].wn >= WT_N - 1) GERR(g, SB_ERR_OVERFLOW); else p.deck[i].wn++; }
@@ -707,6 +755,7 @@ SBD_NI void player_discard(G& g, int order, int index) {  // player.py:57-66
   }
 }
 SBD_NI void player_play(G& g, int order, int index, int pos_pt) {  // player.py:68-77
+  G_LOCAL(g);
   Ply& p = g.pl[order];
   if (index < 0 || index >= p.n_hand) { GERR(g, SB_ERR_INDEX); return; }
   CardRec target = p.hand[index];
@@ -744,6 +793,7 @@ SBD_FI void player_cycle(G& g, int order, int index) { player_discard(g, order, 
 
 // ---------------------------------------------------------------- turn pipeline (board.py:94-145)
 SBD_NI void board_flip(G& g) {  // board.py:94-115
+  G_LOCAL(g);
   g.local_order ^= 1;
   g.pl[0].front_line = (i8)(4 - g.pl[0].front_line);
   g.pl[1].front_line = (i8)(4 - g.pl[1].front_line);
@@ -757,6 +807,7 @@ SBD_NI void board_flip(G& g) {  // board.py:94-115
   while (m) { int t = next_tile(m, true); int id = g.board[t]; g.e[id].x = (u8)(t & 3); g.e[id].y = (u8)(t >> 2); }
 }
 SBD_NI void to_next_turn(G& g) {  // board.py:117-145
+  G_LOCAL(g);
   i8 pts[24], ids[24];
   int n;
   g.phase = PH_TURN_END;
@@ -790,6 +841,7 @@ SBD_NI void to_next_turn(G& g) {  // board.py:117-145
 // ---------------------------------------------------------------- legal actions / step (games/stormbound.py:318-373,528-561)
 SBD_FI void mask_set(u32* m, int a) { m[a >> 5] |= 1u << (a & 31); }
 SBD_NI int legal_mask(const G& g, u32* m) {
+  G_LOCAL(g);
   const Ply& p = g.pl[g.local_order];
   int n_play = 0;
 #pragma unroll
@@ -840,6 +892,7 @@ SBD_FI int place_action(int ci, int pt) {  // Action.to_int PLACE (games/stormbo
   return (y >= 1 && y <= 4) ? 16 * ci + (4 - y) * 4 + PTX(pt) : SB_ACTION_PASS;
 }
 SBD_NI int expert_action(G& g) {
+  G_LOCAL(g);
   u32 m[SB_MASK_WORDS];
   const Ply& p = g.pl[g.local_order];
   legal_mask(g, m);
@@ -907,6 +960,7 @@ SBD_NI int expert_action(G& g) {
 }
 
 SBD_NI void game_step(G& g, int action) {
+  G_LOCAL(g);
   Ply& p = g.pl[g.local_order];
   if (action < 64) {
     int ci = action >> 4, idx = action & 15;
@@ -959,6 +1013,7 @@ SBD_FI void end_of_step(G& g) {
   else { g.n_trig = 0; g.resolving = 0; g.depth = 0; }
 }
 SBD_NI void compact(G& g) {
+  G_LOCAL(g);
   u8 remap[MAXE];
   #pragma unroll 1
   for (int i = 0; i < g.n_ent; i++) remap[i] = 0xFF;

@@ -19,6 +19,7 @@ SBD_FI void store_state(void* dst, const SbState& src) {
 }
 
 SBD_NI void unpack(G& g, const SbState& s) {
+  G_LOCAL(g);
   g.seed_lo = s.seed_lo; g.seed_hi = s.seed_hi; g.turn = s.turn; g.draw = s.draw; g.steps = s.steps;
   g.local_order = s.local_order; g.current_order = s.current_order; g.player_sign = s.player_sign;
   g.phase = s.phase; g.err = s.err; g.done = s.done; g.hist_n = s.hist_n;
@@ -94,6 +95,7 @@ SBD_NI void unpack(G& g, const SbState& s) {
 
 // one memory tree in pre-order (explicit stack; key = owning temple tile, or 0x80 | packed index of the parent copy)
 SBD_NI void pack_mem(const G& g, SbState& s, int root, int root_key, int& nm) {
+  G_LOCAL(g);
   i8 st_idx[NMEM];
   u8 st_key[NMEM];
   int sp = 0;
@@ -123,6 +125,7 @@ SBD_NI void pack_mem(const G& g, SbState& s, int root, int root_key, int& nm) {
   }
 }
 SBD_NI void pack(const G& g, SbState& s) {
+  G_LOCAL(g);
   uint4* z = reinterpret_cast<uint4*>(&s);
 #pragma unroll 8
   for (int i = 0; i < SB_STATE_BYTES / 16; i++) z[i] = make_uint4(0, 0, 0, 0);
@@ -214,6 +217,7 @@ SBD_FI int card_strength_of(const G& g, const CardRec& c) {
 SBD_FI double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
 // returns 0 or SB_ERR_OBS_ID (int(card) raises for UP01-03 anywhere on board, in hand, deck or history: Q12)
 SBD_NI int features(const G& g, double* f) {
+  G_LOCAL(g);
   int err = 0;
   const int lo = g.local_order;
   const Ply& L = g.pl[lo];
@@ -297,6 +301,7 @@ SBD_FI void obs_card_row(const G& g, int* obs, int layer, int row, const CardRec
   OBSI(layer, row, 3) = d.kind == KIND_UNIT ? d.movement : -1;
 }
 SBD_NI int observe(const G& g, int* obs) {
+  G_LOCAL(g);
   int err = 0;
   #pragma unroll 1
   for (int i = 0; i < SB_OBS_INTS; i++) obs[i] = -1;

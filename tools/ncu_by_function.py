@@ -43,7 +43,7 @@ def main():
     cands = sorted(set(re.findall(r"\.text\.(_Z\d+%s\S*)" % base, out)))
     pick = None
     for c in cands:
-        got = re.findall(r"L[bi](\d+)E", c.split("EEv")[0]) if targs else []
+        got = re.findall(r"L[bi](\d+)E", c)[:len(targs)] if targs else []
         if got == targs:
             pick = c
     if pick is None:
