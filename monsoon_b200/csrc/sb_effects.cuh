@@ -19,6 +19,8 @@ SBD_FI int choice_pt(G& g, const i8* l, int n) {
 // then a stable sort (cards/b002.py:20, b008.py:24, b009.py:20, b104.py:19, s101.py:21)
 SBD_NI void keyed_sort(G& g, i8* pts, const i16* k1, int n, bool desc) {
   G_LOCAL(g);
+  P_LOCAL(pts);
+  P_LOCAL(k1);
   double r[22];
   i16 k[22];
   #pragma unroll 1
@@ -55,6 +57,8 @@ SBD_FI int empty_of(const G& g, const i8* in, int n, i8* out) {
 // "frontmost enemy" family: get_targets -> keyed sort on y desc -> take `take`
 SBD_NI int frontmost(G& g, const Target& t, i8* pts) {
   G_LOCAL(g);
+  P_LOCAL(&t);
+  P_LOCAL(pts);
   int n = get_targets(g, CUR(g), t, PT_NONE, pts);
   if (n > 0) {
     i16 ky[22];

@@ -68,14 +68,14 @@ struct Target { u8 kind, side, status, xstatus, has_limit, nonhero, base, pad; u
 #define EF_FIXED 4
 #define EF_SINGLE 8
 #define EF_RPLAY 16
-struct Ent {  // unit.py:8-23 / structure.py:8-16 (statics live in DCard)
+struct __align__(8) Ent {  // unit.py:8-23 / structure.py:8-16 (statics live in DCard); 8-byte aligned: copies are 3 x 64-bit moves
   u8 card, fl;
   i16 strength, dmg;
   u8 st[5];
   u8 move_id, x, y, path_len;
   u8 path[MAXPATH];  // (y+1)*4 + x, y in -1..5
 };
-struct CardRec { u8 card; i8 cost; u8 flags; i8 link; u16 wn; i16 xstr; };
+struct __align__(8) CardRec { u8 card; i8 cost; u8 flags; i8 link; u16 wn; i16 xstr; };  // one 64-bit move per record
 struct Ply {  // player.py:13-37
   i16 base, max_mana, mana;
   i8 front_line;
@@ -85,7 +85,7 @@ struct Ply {  // player.py:13-37
 };
 // cards/b005.py remembered deep copies.  parent < 0: a memory of the live temple entity `b005`; parent >= 0: a
 // memory held BY the remembered temple copy mem[parent] (its own ability_remembered); parent index < own index.
-struct Mem { i8 b005; u8 pos, card, fl; i16 strength; u8 st[5]; i8 parent; };
+struct __align__(8) Mem { i8 b005; u8 pos, card, fl; i16 strength; u8 st[5]; i8 parent; };  // 16 bytes
 
 struct G {
   Ent e[MAXE];
@@ -101,7 +101,7 @@ struct G {
   u32 occ;    // occupied-tile bitmask, mirrors board[]
   u32 own1;   // occupied tiles whose entity belongs to order 1 (bits of empty tiles are don't-care)
   u32 strc;   // occupied tiles holding a structure (bits of empty tiles are don't-care)
-  u8 trig[MAXTRIG];  // entity id | has_source << 7
+  __align__(8) u8 trig[MAXTRIG];  // entity id | has_source << 7   (8-byte aligned: end of the block copy_g moves)
   Mem mem[NMEM];
   const DCard* cards;   // shared-memory copy
   const double* wt;     // f^n(1) table in global memory
@@ -112,8 +112,10 @@ struct G {
 // turns the generic 64-bit loads/stores through `G&` into local-space ones (no per-access descriptor moves).
 #ifdef __CUDA_ARCH__
 #define G_LOCAL(g) __builtin_assume(__isLocal(&(g)))
+#define P_LOCAL(p) __builtin_assume(__isLocal(p))  // same for Target objects and result lists (always caller locals)
 #else
 #define G_LOCAL(g) ((void)0)
+#define P_LOCAL(p) ((void)0)
 #endif
 
 SBD_FI int PTX(int pt) { return pt >= 20 ? -1 : (pt & 3); }
@@ -243,6 +245,8 @@ SBD_FI bool ent_matches_filters(const G& g, const Ent& e, const Target& t) {
 // base_passes: base points survive the region filter when include_base (board.py:215,262,276,294).
 SBD_NI int get_targets_region(const G& g, int pov, const Target& t, int exclude_pt, u32 region, bool base_passes, i8* out) {
   G_LOCAL(g);
+  P_LOCAL(&t);
+  P_LOCAL(out);
   int n = 0;
   bool pov_local = (pov == g.local_order);
   // side and kind are decided by bitmask algebra (own1 = tiles whose entity belongs to order 1, strc =
@@ -332,6 +336,7 @@ SBD_FI void sort_pts_by_y(i8* a, int n, bool desc) {  // stable insertion sort o
 // board.py:206-234.  toward_enemy: front tiles; else behind tiles.  t == nullptr: the plain tile list.
 SBD_NI int column_tiles(const G& g, int x, int y, int pov, const Target* t, bool front, i8* out) {
   G_LOCAL(g);
+  P_LOCAL(out);
   bool pov_local = (pov == g.local_order);
   bool up = (pov_local == front);  // decreasing y
   int n = 0;
@@ -842,6 +847,7 @@ SBD_NI void to_next_turn(G& g) {  // board.py:117-145
 SBD_FI void mask_set(u32* m, int a) { m[a >> 5] |= 1u << (a & 31); }
 SBD_NI int legal_mask(const G& g, u32* m) {
   G_LOCAL(g);
+  P_LOCAL(m);
   const Ply& p = g.pl[g.local_order];
   int n_play = 0;
 #pragma unroll

@@ -374,12 +374,38 @@ SBD_FI double score_delta(const double* w, const double* fc, const double* fn) {
   double rp = eff < -0.3 ? __dmul_rn(fabs(eff), 0.2) : 0.0;
   return __dsub_rn(__dsub_rn(-d, d), rp);
 }
-// One decision for the game whose packed base state sits in shared memory.  Every lane forks the base,
+// The base state of a decision is either the packed 512-byte record (k_select_action: states come from the caller
+// one decision at a time) or a raw image of the working set G kept in shared memory for the whole game
+// (k_rollout_heuristic).  The image avoids the pack / unpack of every decision: ncu on the packed version showed
+// unpack 18 % and pack 14 % (one lane) of all warp instructions.  copy_g moves the live parts 64 bits at a time:
+// the entity pool up to n_ent, the block [board .. strc] and the Temple-of-Time memories up to n_mem; the trigger
+// stack is empty between steps and the table pointers belong to each copy.
+SBD_NI void copy_g(G& dst, const G& src) {
+  typedef unsigned long long u64;
+  static_assert(offsetof(G, board) % 8 == 0 && offsetof(G, trig) % 8 == 0 && sizeof(Ent) % 8 == 0 && sizeof(Mem) % 8 == 0, "copy_g layout");
+  const u64* s8 = reinterpret_cast<const u64*>(&src);
+  u64* d8 = reinterpret_cast<u64*>(&dst);
+  const int ne = src.n_ent * (int)(sizeof(Ent) / 8);
+  #pragma unroll 4
+  for (int i = 0; i < ne; i++) d8[i] = s8[i];
+  #pragma unroll 8
+  for (int i = (int)(offsetof(G, board) / 8); i < (int)(offsetof(G, trig) / 8); i++) d8[i] = s8[i];
+  const int m0 = (int)(offsetof(G, mem) / 8), nm = src.n_mem * (int)(sizeof(Mem) / 8);
+  #pragma unroll 1
+  for (int i = 0; i < nm; i++) d8[m0 + i] = s8[m0 + i];
+}
+SBD_FI void base_load(G& g, const SbState& b) { unpack(g, b); }
+SBD_FI void base_store(SbState& b, G& g) { pack(g, b); }
+SBD_FI void base_load(G& g, const G& b) { copy_g(g, b); }
+SBD_FI void base_store(G& b, G& g) { end_of_step(g); copy_g(b, g); }  // same lazy compaction / overflow rules as the random rollout
+
+// One decision for the game whose base state sits in shared memory.  Every lane forks the base,
 // applies its candidate(s), scores them; returns the warp-wide best action.  If `commit`, the lane that
 // owns the winner leaves the post-action state packed in `base` (the fork becomes the game).
-SBD_NI int decide(G& g, SbState* base, const double* w, double* scores_out, bool commit) {
+template <class Base>
+SBD_NI int decide(G& g, Base* base, const double* w, double* scores_out, bool commit) {
   const int lane = threadIdx.x & 31;
-  unpack(g, *base);
+  base_load(g, *base);
   u32 m[SB_MASK_WORDS];
   legal_mask(g, m);
   double fc[SB_N_FEATURES], fn[SB_N_FEATURES];
@@ -406,7 +432,7 @@ SBD_NI int decide(G& g, SbState* base, const double* w, double* scores_out, bool
     }
     if (a < 0) continue;
     if (n_legal == 1 && !scores_out) { best.score = 0.0; best.action = a; break; }  // forced move: argmax of one
-    if (dirty) unpack(g, *base);
+    if (dirty) base_load(g, *base);
     game_step(g, a);
     dirty = true; last = a;
     double sc = 0.0;
@@ -422,8 +448,8 @@ SBD_NI int decide(G& g, SbState* base, const double* w, double* scores_out, bool
     __syncwarp();  // everybody is done reading the base
     bool owner = (win.action >= 0) ? (best.action == win.action) : (lane == 0);
     if (owner) {
-      if (last != action) { unpack(g, *base); game_step(g, action); }
-      pack(g, *base);
+      if (last != action) { base_load(g, *base); game_step(g, action); }
+      base_store(*base, g);
     }
     __syncwarp();
   }
@@ -457,18 +483,24 @@ __global__ void __launch_bounds__(WPC * 32) k_rollout_heuristic(int n, u8* state
                                                                 const int* idx_first, const int* idx_second, int max_steps,
                                                                 i8* result, int* steps_out, const DCard* cards, const double* wt) {
   __shared__ DCard s_cards[SBC_COUNT];
-  __shared__ __align__(16) SbState s_base[WPC];
+  extern __shared__ __align__(16) unsigned char s_dyn[];  // WPC working-set images (sizeof(G) each)
+  G* s_base = reinterpret_cast<G*>(s_dyn);
   stage_cards(s_cards, cards);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gi = blockIdx.x * WPC + warp;
   const bool has_game = gi < n;
   if (!BSYNC && !has_game) return;
-  SbState* base = &s_base[warp];
+  G* base = &s_base[warp];
   G g;
   init_g(g, s_cards, wt);
   double wf[SB_N_FEATURES], ws[SB_N_FEATURES];
   if (has_game) {
-    reinterpret_cast<uint4*>(base)[lane] = reinterpret_cast<const uint4*>(states + (size_t)gi * SB_STATE_BYTES)[lane];
+    if (lane == 0) {  // packed record -> working set -> shared image, once per game
+      __align__(16) SbState s;
+      load_state(s, states + (size_t)gi * SB_STATE_BYTES);
+      unpack(g, s);
+      copy_g(*base, g);
+    }
     const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
     const double* ps = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
     for (int k = 0; k < SB_N_FEATURES; k++) { wf[k] = pf[k]; ws[k] = ps[k]; }
@@ -491,8 +523,14 @@ __global__ void __launch_bounds__(WPC * 32) k_rollout_heuristic(int n, u8* state
       res = (l1 && !l0) ? 0 : (l0 && !l1) ? 1 : -1;
     }
     __syncwarp();
-    reinterpret_cast<uint4*>(states + (size_t)gi * SB_STATE_BYTES)[lane] = reinterpret_cast<const uint4*>(base)[lane];
-    if (lane == 0) { if (result) result[gi] = (i8)res; if (steps_out) steps_out[gi] = k; }
+    if (lane == 0) {
+      __align__(16) SbState s;
+      copy_g(g, *base);
+      pack(g, s);
+      store_state(states + (size_t)gi * SB_STATE_BYTES, s);
+      if (result) result[gi] = (i8)res;
+      if (steps_out) steps_out[gi] = k;
+    }
   }
 }
 
@@ -651,6 +689,11 @@ int sb_create(int device, SbHandle** out) {
   }
   CK(cudaMalloc(&h->d_wt, sizeof wt));
   CK(cudaMemcpy(h->d_wt, wt, sizeof wt, cudaMemcpyHostToDevice));
+  // the heuristic rollout keeps one working-set image per warp in dynamic shared memory (up to 32 x sizeof(G) = 62 KB)
+  CK(cudaFuncSetAttribute(k_rollout_heuristic<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * sizeof(G))));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * sizeof(G))));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(G))));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(G))));
   CK(cudaMalloc(&h->d_queue, sizeof(int)));
   {  // deck pools: dir(cards) order == card index order; own faction + NEUTRAL (utils.py:74-84)
     static u8 pools[5 * POOL_W];
@@ -824,9 +867,10 @@ int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   int hw = h->heur_wpc;
-  if (hw < 0) hw = n >= 49152 ? 32 : 4;  // auto (tools/sweep_heur.py)
-#define HEUR(W, B) k_rollout_heuristic<W, B><<<grid_for(n, W), W * 32, 0, st>>>(n, states_d, w_first_d, w_second_d, idx_first_d, idx_second_d, \
-                                                                             max_steps, (i8*)result_d, steps_d, h->d_cards, h->d_wt)
+  if (hw < 0) hw = 4;  // auto (tools/sweep_heur.py): with the shared working-set image independent warps win at every batch size;
+                       // limiting resident threads to fit L2 only loses (tools/sweep_heur_resident.py, removed knob)
+#define HEUR(W, B) k_rollout_heuristic<W, B><<<grid_for(n, W), W * 32, W * sizeof(G), st>>>(n, states_d, w_first_d, w_second_d, idx_first_d, \
+                                                                                       idx_second_d, max_steps, (i8*)result_d, steps_d, h->d_cards, h->d_wt)
   if (hw >= 32) HEUR(32, true); else if (hw >= 16) HEUR(16, true); else if (hw >= 8) HEUR(8, true); else HEUR(4, false);
 #undef HEUR
   LAUNCH_CHECK();

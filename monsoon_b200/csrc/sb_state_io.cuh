@@ -218,6 +218,7 @@ SBD_FI double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
 // returns 0 or SB_ERR_OBS_ID (int(card) raises for UP01-03 anywhere on board, in hand, deck or history: Q12)
 SBD_NI int features(const G& g, double* f) {
   G_LOCAL(g);
+  P_LOCAL(f);
   int err = 0;
   const int lo = g.local_order;
   const Ply& L = g.pl[lo];
