@@ -33,13 +33,14 @@ SBD_NI void unpack(G& g, const SbState& s) {
     p.base = sp.base; p.max_mana = sp.max_mana; p.mana = sp.mana; p.front_line = sp.front_line;
     p.replacable = (sp.flags & SB_PF_REPLACABLE) != 0; p.leftmost = (sp.flags & SB_PF_LEFTMOST) != 0;
     p.n_hand = sp.n_hand; p.n_deck = sp.n_deck; p.faction = sp.faction;
+    const int nh = sp.n_hand < SB_HAND_MAX ? sp.n_hand : SB_HAND_MAX, nd = sp.n_deck < SB_DECK_MAX ? sp.n_deck : SB_DECK_MAX;
     #pragma unroll 1
-    for (int i = 0; i < SB_HAND_MAX; i++) {
+    for (int i = 0; i < nh; i++) {  // records beyond n_hand / n_deck are never read
       CardRec& c = p.hand[i];
       c.card = sp.hand_card[i]; c.cost = sp.hand_cost[i]; c.flags = sp.hand_flags[i]; c.link = -1; c.wn = 0; c.xstr = 0;
     }
     #pragma unroll 1
-    for (int i = 0; i < SB_DECK_MAX; i++) {
+    for (int i = 0; i < nd; i++) {
       CardRec& c = p.deck[i];
       c.card = sp.deck_card[i]; c.cost = sp.deck_cost[i]; c.flags = sp.deck_flags[i]; c.link = -1; c.wn = sp.deck_wn[i]; c.xstr = 0;
     }
@@ -170,7 +171,7 @@ SBD_NI void pack(const G& g, SbState& s) {
   u8* x = s.ext;
   int nm = 0;
   #pragma unroll 1
-  for (int tile = 0; tile < SB_N_TILES; tile++) {  // canonical order: temples in tile order, each memory followed by its subtree
+  for (int tile = 0; tile < SB_N_TILES && g.n_mem; tile++) {  // canonical order: temples in tile order, each memory followed by its subtree
     int bid = g.board[tile];
     if (bid < 0 || g.e[bid].card != SBC_B005) continue;
     #pragma unroll 1
@@ -180,7 +181,7 @@ SBD_NI void pack(const G& g, SbState& s) {
   x[0] = (u8)nm;
   int no = 0;
   #pragma unroll 1
-  for (int o = 0; o < 2; o++) for (int where = 0; where < 2; where++) {
+  for (int o = 0; o < 2 && g.n_obj; o++) for (int where = 0; where < 2; where++) {  // n_obj is an upper bound: 0 = no such record
     const Ply& p = g.pl[o];
     int cnt = where ? p.n_deck : p.n_hand;
     #pragma unroll 1

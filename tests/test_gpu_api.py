@@ -122,3 +122,41 @@ def test_deck_generation_matches_oracle_at_scale(engine, oracle):
             want = oracle.generate_decks(int(seeds[i]), 17, mode, keep, q, arch, fac[i] if mode == 3 else [2, 4])
             assert np.array_equal(decks[i], want), (mode, i)
 
+
+
+def test_empty_ragged_and_rejected_inputs(engine):
+    """Empty batches are no-ops, a batch that is not a multiple of any CTA / warp size is handled exactly, finished
+    games are left alone by the rollouts, and malformed calls fail loudly instead of launching."""
+    from monsoon_b200 import _lib
+    dev = engine.device
+    empty = torch.empty((0, 512), dtype=torch.uint8, device=dev)
+    assert engine.legal_mask(empty).shape == (0, 5)
+    assert engine.rollout_random(empty, 400).numel() == 0
+    assert engine.expert_action(empty).numel() == 0
+    res, steps = engine.rollout_heuristic(empty, torch.zeros((0, 10), dtype=torch.float64, device=dev),
+                                          torch.zeros((0, 10), dtype=torch.float64, device=dev))
+    assert res.numel() == 0 and steps.numel() == 0
+    d, f = engine.generate_decks(np.zeros(0, dtype=np.int64), 0, 0, 12, 0.0, np.arange(1, 25, dtype=np.uint8), [1, 2])
+    assert d.shape == (0, 2, 12) and f.shape == (0, 2)
+    # ragged: 37 and 1 games through every per-game kernel shape; results do not depend on the batch they ran in
+    seeds = torch.arange(37, dtype=torch.int64, device=dev) + 9000
+    st37 = engine.reset(seeds)
+    s37 = engine.rollout_random(st37, 400)
+    st1 = engine.reset(seeds[36:37])
+    s1 = engine.rollout_random(st1, 400)
+    assert int(s1[0]) == int(s37[36]) and torch.equal(st1[0], st37[36])
+    # finished games: a second rollout takes zero steps and leaves the records untouched
+    before = st37.clone()
+    again = engine.rollout_random(st37, 400)
+    assert int(again.sum()) == 0 and torch.equal(before, st37)
+    w = torch.rand((37, 10), dtype=torch.float64, device=dev)
+    res, steps = engine.rollout_heuristic(st37, w, w)
+    assert int(steps.sum()) == 0 and torch.equal(before, st37)
+    # rejected calls
+    with pytest.raises(_lib.SbError):
+        engine.generate_decks(seeds, 0, 3)  # fully random decks need per-game factions
+    big = torch.zeros((8, 65), dtype=torch.float64, device=dev)
+    with pytest.raises(_lib.SbError):
+        engine.es_offspring(1, 0, 4, 4, 0.1, 0.01, 1e-5, big, big.clone())  # more than 64 features
+    with pytest.raises(_lib.SbError):
+        engine.es_select(9, np.zeros(8), big[:, :10].contiguous(), big[:, :10].contiguous())  # mu > rows
