@@ -326,6 +326,8 @@ __global__ void __launch_bounds__(TPB) k_rollout_random(int n, u8* states, int m
           a = pick_action(g);
           if (a == SB_ACTION_PASS) { at_pass = true; a = -1; }
         }
+        // CTA-wide vote per round in CTA-synchronous mode: measured against warp votes + one barrier per turn
+        // (tools/sweep_phase.py, removed): the shared instruction stream is worth more than the barrier waits (343 vs 300 M)
         if (!(BSYNC ? __syncthreads_or(a >= 0) : __any_sync(FULL, a >= 0))) break;
         if (a >= 0) {
           game_step(g, a);
