@@ -198,8 +198,7 @@ SBD_FI int next_tile(u32& m, bool ascending) {
   m &= ~(1u << t);
   return t;
 }
-SBD_NI void calc_front_line(G& g, int order) {  // board.py:78-92
-  G_LOCAL(g);
+SBD_FI void calc_front_line(G& g, int order) {  // board.py:78-92
   const bool local = order == g.local_order;
   int fl = local ? 4 : 0;
   const u32 m = g.occ & (order ? g.own1 : ~g.own1);  // this side's entities: first (local) / last (remote) occupied row
@@ -405,8 +404,7 @@ SBD_FI void push_trigger(G& g, int id, int has_source) {
   if (g.n_trig >= MAXTRIG) { GERR(g, SB_ERR_OVERFLOW); return; }
   g.trig[g.n_trig++] = (u8)(id | (has_source ? 0x80 : 0));
 }
-SBD_NI void pop_trigger(G& g) {
-  G_LOCAL(g);
+SBD_FI void pop_trigger(G& g) {
   if (g.n_trig == 0 || g.resolving) return;
   u8 t = g.trig[--g.n_trig];
   ability(g, t & 0x7F, PT_NONE, t >> 7);
@@ -422,8 +420,7 @@ SBD_NI void ability(G& g, int id, int pos_pt, int has_source) {
   pop_trigger(g);
   g.depth--;
 }
-SBD_NI void spell_ability(G& g, int card, int caster, int pos_pt) {
-  G_LOCAL(g);
+SBD_FI void spell_ability(G& g, int card, int caster, int pos_pt) {
   if (g.depth > MAXDEPTH) { GERR(g, SB_ERR_DEPTH); return; }
   g.depth++;
   g.resolving = 1;
@@ -468,8 +465,7 @@ SBD_NI int deal_damage(G& g, int id, int amount, int pending, int has_source) {
   else if (!ent_struct(e) && e.strength > 0 && CARD(g, e.card).trigger == TR_AFTER_SURVIVING) { push_trigger(g, id, has_source); pop_trigger(g); }
   return amount;
 }
-SBD_NI int deal_damage_pt(G& g, int pt, int amount, int has_source) {  // board.at(point).deal_damage(...)
-  G_LOCAL(g);
+SBD_FI int deal_damage_pt(G& g, int pt, int amount, int has_source) {  // board.at(point).deal_damage(...)
   if (pt == PT_BASE_LOCAL) return player_damage(g, g.local_order, amount);
   if (pt == PT_BASE_REMOTE) return player_damage(g, 1 - g.local_order, amount);
   int id = at_pt(g, pt);
@@ -479,8 +475,7 @@ SBD_NI int deal_damage_pt(G& g, int pt, int amount, int has_source) {  // board.
 
 // ---------------------------------------------------------------- movement (unit.py:66-203, 277-382)
 SBD_FI u8 enc_xy(int x, int y) { return (u8)((y + 1) * 4 + x); }
-SBD_NI void set_path(G& g, int id, int on_play, int extra_movement) {  // unit.py:78-122
-  G_LOCAL(g);
+SBD_FI void set_path_inl(G& g, int id, int on_play, int extra_movement) {  // unit.py:78-122; inlined where a move follows at once
   Ent& e = g.e[id];
   u8 dest[MAXPATH];
   int nd = 0;
@@ -522,6 +517,10 @@ SBD_NI void set_path(G& g, int id, int on_play, int extra_movement) {  // unit.p
   e.path_len = (u8)nd;
 }
 
+SBD_NI void set_path(G& g, int id, int on_play, int extra_movement) {  // out-of-line copy for the rare callers
+  G_LOCAL(g);
+  set_path_inl(g, id, on_play, extra_movement);
+}
 SBD_NI void unit_move(G& g, int id) {  // unit.py:124-203
   G_LOCAL(g);
   Ent& e = g.e[id];
@@ -583,11 +582,10 @@ SBD_NI void unit_move(G& g, int id) {  // unit.py:124-203
   }
   g.depth--;
 }
-SBD_NI void unit_play(G& g, int id, int x, int y) {  // unit.py:66-76
-  G_LOCAL(g);
+SBD_FI void unit_play(G& g, int id, int x, int y) {  // unit.py:66-76
   g.e[id].fl |= EF_RPLAY;
   set_xy(g, x, y, id);
-  set_path(g, id, 1, 0);
+  set_path_inl(g, id, 1, 0);
   if (CARD(g, g.e[id].card).trigger == TR_ON_PLAY) ability(g, id, PT_NONE, 1);
   unit_move(g, id);
   g.e[id].fl &= ~EF_RPLAY;
@@ -839,7 +837,7 @@ SBD_NI void to_next_turn(G& g) {  // board.py:117-145
   #pragma unroll 1
   for (int i = 0; i < n; i++) ids[i] = (i8)at_pt(g, pts[i]);
   #pragma unroll 1
-  for (int i = 0; i < n; i++) { set_path(g, ids[i], 0, 0); unit_move(g, ids[i]); }  // snapshot incl. ghosts (Q21)
+  for (int i = 0; i < n; i++) { set_path_inl(g, ids[i], 0, 0); unit_move(g, ids[i]); }  // snapshot incl. ghosts (Q21)
   g.phase = PH_PLAY;
 }
 

@@ -25,6 +25,29 @@ def symbols(so, kernel_mangled):
     return sorted(set(syms))
 
 
+def calibrate(body, syms):
+    """Section offset of the first listed instruction.  The page does not always start at section offset 0: every
+    CALL.REL target is a function start, so the shift is the one that maps most call targets onto symbol values."""
+    a0 = int(body[0][0], 16)
+    targets = set()
+    for r in body:
+        m = re.search(r"CALL\.REL\.NOINC (0x[0-9a-f]+)", r[1])
+        if m:
+            targets.add(int(m.group(1), 16) - a0)
+    starts = {v for v, _sz, _n in syms}
+    best, best_hits = 0, -1
+    for t in targets:
+        for v in starts:
+            d = v - t
+            hits = sum(1 for x in targets if x + d in starts)
+            if hits > best_hits:
+                best, best_hits = d, hits
+    if targets and best_hits < 0.9 * len(targets):
+        sys.stderr.write("WARNING: only %d of %d call targets land on function symbols -- is this the library the capture "
+                         "was taken with?\n" % (best_hits, len(targets)))
+    return best
+
+
 def demangle(n):
     m = re.match(r"_Z(\d+)", n)
     return n[m.end():m.end() + int(m.group(1))] if m else n
@@ -50,7 +73,7 @@ def main():
         pick = cands[0]
     syms = symbols(so, pick)
     body = rows[2:]
-    a0 = int(body[0][0], 16)
+    a0 = int(body[0][0], 16) - calibrate(body, syms)
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     agg = collections.defaultdict(lambda: collections.Counter())
     for r in body:

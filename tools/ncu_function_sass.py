@@ -3,13 +3,15 @@
   python tools/ncu_function_sass.py src.csv lib.so <kernel .text section mangled name> <function substring>
 Columns: offset, executions per call (first instruction = calls), average active threads, SASS.
 """
-import csv, re, subprocess, sys
+import csv, os, re, subprocess, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from ncu_by_function import calibrate, symbols
 src, so, section, fn = sys.argv[1:5]
 rows = list(csv.reader(open(src)))
 hdr = rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 body = rows[2:]
-a0 = int(body[0][0], 16)
+a0 = int(body[0][0], 16) - calibrate(body, symbols(so, section))
 out = subprocess.run(["cuobjdump", "-elf", so], capture_output=True, text=True).stdout
 sym = None
 for line in out.splitlines():
