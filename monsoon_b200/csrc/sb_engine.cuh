@@ -1035,9 +1035,9 @@ SBD_NI void compact(G& g) {
     g.board[t] = (i8)n;
     n++;
   }
-  // frozen strength of board-instance card records whose object left the board
+  // frozen strength of board-instance card records whose object left the board (n_obj is an upper bound: 0 = none)
   #pragma unroll 1
-  for (int o = 0; o < 2; o++) {
+  for (int o = 0; o < 2 && g.n_obj; o++) {
     Ply& p = g.pl[o];
     #pragma unroll 1
     for (int i = 0; i < p.n_hand; i++) if (p.hand[i].link >= 0) {
@@ -1070,7 +1070,7 @@ SBD_NI void compact(G& g) {
   // what would not fit the packed layout is an overflow there too (keeps rollouts == step-per-launch)
   int nobj = 0;
   #pragma unroll 1
-  for (int o = 0; o < 2; o++) {
+  for (int o = 0; o < 2 && g.n_obj; o++) {
     #pragma unroll 1
     for (int i = 0; i < g.pl[o].n_hand; i++) nobj += (g.pl[o].hand[i].flags & SB_CF_OBJ) != 0;
     #pragma unroll 1
