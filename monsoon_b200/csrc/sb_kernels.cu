@@ -598,7 +598,7 @@ static void launch_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max
   }
   unsigned long long* ch = (unsigned long long*)chain_d;
   int bs = h->block_sync;
-  if (bs < 0) bs = n >= 196608 ? 1024 : n >= 49152 ? 512 : 0;  // auto (tools/sweep_bsync.py): pays off once the chip is full
+  if (bs < 0) bs = n >= 90000 ? 1024 : n >= 57000 ? 512 : n >= 30000 ? 128 : 0;  // auto (tools/sweep_bsync.py): pays off once the chip is full
   // lane refill: persistent grid of resident CTAs, lanes take games from a counter (batches beyond the resident lanes)
   int* q = nullptr;
   const int resident = h->sm_count * 1024;  // 64 registers x 1024 threads fill one SM's register file

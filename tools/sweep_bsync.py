@@ -8,7 +8,7 @@ sizes = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "4096,65536,2621
 for n in sizes:
     seeds = torch.arange(n, dtype=torch.int64, device=eng.device) + 12345
     ref = None
-    for bs in (0, 512, 1024, -1):
+    for bs in (0, 128, 256, 512, 1024, -1):
         eng.lib.sb_set_option(eng.h, b"block_sync", bs)
         best = 1e9
         for rep in range(3):
