@@ -113,9 +113,11 @@ struct G {
 #ifdef __CUDA_ARCH__
 #define G_LOCAL(g) __builtin_assume(__isLocal(&(g)))
 #define P_LOCAL(p) __builtin_assume(__isLocal(p))  // same for Target objects and result lists (always caller locals)
+#define P_SHARED(p) __builtin_assume(__isShared(p))  // the card table every CTA stages in shared memory
 #else
 #define G_LOCAL(g) ((void)0)
 #define P_LOCAL(p) ((void)0)
+#define P_SHARED(p) ((void)0)
 #endif
 
 SBD_FI int PTX(int pt) { return pt >= 20 ? -1 : (pt & 3); }
@@ -123,7 +125,7 @@ SBD_FI int PTY(int pt) { return pt == PT_BASE_REMOTE ? -1 : pt == PT_BASE_LOCAL 
 SBD_FI int PT(int x, int y) { return y * 4 + x; }
 SBD_FI bool valid_xy(int x, int y) { return (unsigned)x <= 3u && (unsigned)y <= 4u; }
 SBD_FI bool is_base_pt(int pt) { return pt >= 20; }
-SBD_FI const DCard& CARD(const G& g, int card) { return g.cards[card]; }
+SBD_FI const DCard& CARD(const G& g, int card) { const DCard* c = g.cards; P_SHARED(c); return c[card]; }
 SBD_FI int ent_owner(const Ent& e) { return e.fl & EF_OWNER; }
 SBD_FI bool ent_struct(const Ent& e) { return e.fl & EF_STRUCT; }
 
@@ -220,26 +222,6 @@ SBD_FI Target card_target(const DCard& c) {
   t.has_limit = c.t_limit >= 0; t.limit = c.t_limit; t.nonhero = (c.flags & DCF_TNONHERO) != 0; t.base = (c.flags & DCF_TBASE) != 0;
   return t;
 }
-// the rare filters of board.py:170-179 (side and kind are already decided by the bitmasks of the caller)
-SBD_FI bool ent_matches_filters(const G& g, const Ent& e, const Target& t) {
-  if (t.has_limit && e.strength > t.limit) return false;
-  if (ent_struct(e)) return true;  // structures only honour strength_limit (board.py:179)
-  u16 types = CARD(g, e.card).types;
-  if (t.types && !(types & t.types)) return false;
-  if (t.xtypes && (types & t.xtypes)) return false;
-  if (t.nonhero && (types & (1 << UT_HERO))) return false;
-  if (t.status) {
-    bool any = false;
-#pragma unroll 1
-    for (int s = 0; s < 5; s++) if ((t.status >> s & 1) && e.st[s]) any = true;
-    if (!any) return false;
-  }
-  if (t.xstatus) {
-#pragma unroll 1
-    for (int s = 0; s < 5; s++) if ((t.xstatus >> s & 1) && e.st[s]) return false;
-  }
-  return true;
-}
 // region = bitmask over tiles (bit t) that a tile must belong to; 0xFFFFF = whole board.
 // base_passes: base points survive the region filter when include_base (board.py:215,262,276,294).
 SBD_NI int get_targets_region(const G& g, int pov, const Target& t, int exclude_pt, u32 region, bool base_passes, i8* out) {
@@ -247,7 +229,7 @@ SBD_NI int get_targets_region(const G& g, int pov, const Target& t, int exclude_
   P_LOCAL(&t);
   P_LOCAL(out);
   int n = 0;
-  bool pov_local = (pov == g.local_order);
+  const bool pov_local = (pov == g.local_order);
   // side and kind are decided by bitmask algebra (own1 = tiles whose entity belongs to order 1, strc =
   // structure tiles); the per-entity loop only sees real candidates and usually checks strength > 0 alone
   u32 m = g.occ & region;
@@ -257,13 +239,35 @@ SBD_NI int get_targets_region(const G& g, int pov, const Target& t, int exclude_
     m &= (t.side == TS_FRIENDLY) ? mine : ~mine;
   }
   if (t.kind == TK_UNIT) m &= ~g.strc; else if (t.kind == TK_STRUCTURE) m &= g.strc;
-  const bool filters = t.has_limit | t.nonhero | t.status | t.xstatus | (t.types != 0) | (t.xtypes != 0);
+  // the rare filters of board.py:170-179, read once (the stores to `out` would otherwise force a reload per candidate)
+  const bool has_limit = t.has_limit != 0;
+  const int limit = t.limit;
+  const u32 want_types = t.types, bad_types = (u32)t.xtypes | (t.nonhero ? (1u << UT_HERO) : 0u);
+  const u32 want_status = t.status, bad_status = t.xstatus;
+  const bool filters = has_limit | (want_types != 0) | (bad_types != 0) | (want_status != 0) | (bad_status != 0);
+  const DCard* cards = g.cards;
+  P_SHARED(cards);
   #pragma unroll 1
   while (m) {
-    int tile = next_tile(m, pov_local);
+    const int tile = next_tile(m, pov_local);
     const Ent& e = g.e[g.board[tile]];
-    if (e.strength <= 0) continue;  // board.py:164
-    if (filters && !ent_matches_filters(g, e, t)) continue;
+    const int str = e.strength;
+    if (str <= 0) continue;  // board.py:164
+    if (filters) {
+      if (has_limit && str > limit) continue;
+      if (!ent_struct(e)) {  // structures only honour strength_limit (board.py:179)
+        if (want_types | bad_types) {
+          const u32 types = cards[e.card].types;
+          if ((want_types && !(types & want_types)) || (types & bad_types)) continue;
+        }
+        if (want_status | bad_status) {
+          u32 have = 0;
+#pragma unroll
+          for (int k = 0; k < 5; k++) have |= (e.st[k] ? 1u : 0u) << k;
+          if ((want_status && !(have & want_status)) || (have & bad_status)) continue;
+        }
+      }
+    }
     out[n++] = (i8)tile;
   }
   if (t.base && base_passes) {
