@@ -25,8 +25,8 @@ sys.path[:0] = [ROOT]
 
 B_STEP = 2 * 512 + 1 + 20 + 2  # algorithmic bytes per env step: state in+out, action, mask, reward/done
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_rollout_random launch at the named workload, from the
-# ncu --set full capture profiles/r1_rollout_4096_final_metrics.txt (19.50 MB read + 6.12 MB written)
-NCU_TRAFFIC_BYTES_PER_LAUNCH_4096 = 25_627_392
+# ncu --set full capture profiles/r1_rollout_4096_final_metrics.txt (19.01 MB read + 5.63 MB written)
+NCU_TRAFFIC_BYTES_PER_LAUNCH_4096 = 24_646_656
 METRIC = "env_steps_per_sec"
 WORKLOAD = "4096 parallel games/GPU, uniform-random legal agents, default decks, played to completion (max 400 steps)"
 
