@@ -174,11 +174,13 @@ __global__ void __launch_bounds__(TPB_GAME) k_expert_action(int n, u8* states, u
 }
 
 __global__ void __launch_bounds__(TPB_GAME) k_step(int n, u8* states, const u8* actions, i8* reward, u8* done, u8* err,
-                                                   u32* next_masks, const DCard* cards, const double* wt) {
+                                                   u32* next_masks, const DCard* cards, const double* wt, int gpw) {
   __shared__ DCard s_cards[SBC_COUNT];
   stage_cards(s_cards, cards);
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  // gpw games per warp on consecutive lanes, like the rollout kernel: small batches spread over more warps / SMs
+  const int lane = threadIdx.x & 31;
+  const int i = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * gpw + lane;
+  if (lane >= gpw || i >= n) return;
   G g;
   init_g(g, s_cards, wt);
   __align__(16) SbState s;  // 128-bit moves
@@ -586,16 +588,17 @@ static int fail(SbHandle* h, cudaError_t e, const char* what) {
 #define LAUNCH_CHECK() do { h->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(h, e_, "kernel launch"); } while (0)
 
 static inline int grid_for(int n, int per_cta) { return (n + per_cta - 1) / per_cta; }
+static inline int games_per_warp(const SbHandle* h, int n) {
+  if (h->gpw > 0 && h->gpw <= 32) return h->gpw;
+  // auto (measured, tools/sweep_gpw.py): aim at ~3.5 warps per SM while the batch is small
+  // (4096 games -> 8 per warp, 8192 -> 16, 16384 and up -> full warps)
+  const int per_warp = (2 * n + h->sm_count * 7 - 1) / (h->sm_count * 7);
+  return per_warp > 16 ? 32 : per_warp > 8 ? 16 : 8;
+}
 template <bool DIGEST>
 static void launch_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max_steps, int32_t* steps_d, uint64_t* chain_d,
                                   cudaStream_t st) {
-  int gpw = h->gpw;
-  if (gpw <= 0 || gpw > 32) {
-    // auto (measured, tools/sweep_gpw.py): aim at ~3.5 warps per SM while the batch is small
-    // (4096 games -> 8 per warp, 8192 -> 16, 16384 and up -> full warps)
-    const int per_warp = (2 * n + h->sm_count * 7 - 1) / (h->sm_count * 7);
-    gpw = per_warp > 16 ? 32 : per_warp > 8 ? 16 : 8;
-  }
+  const int gpw = games_per_warp(h, n);
   unsigned long long* ch = (unsigned long long*)chain_d;
   int bs = h->block_sync;
   if (bs < 0) bs = n >= 90000 ? 1024 : n >= 57000 ? 512 : n >= 30000 ? 128 : 0;  // auto (tools/sweep_bsync.py): pays off once the chip is full
@@ -819,8 +822,9 @@ int sb_expert_action(SbHandle* h, int n, uint8_t* states_d, uint8_t* actions_d, 
 int sb_step(SbHandle* h, int n, uint8_t* states_d, const uint8_t* actions_d, int8_t* reward_d, uint8_t* done_d, uint8_t* err_d,
             uint32_t* next_masks_d, void* stream) {
   if (n <= 0) return 0;
-  k_step<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, actions_d, (i8*)reward_d, done_d, err_d, next_masks_d,
-                                                                       h->d_cards, h->d_wt);
+  const int gpw = games_per_warp(h, n);
+  k_step<<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, actions_d, (i8*)reward_d, done_d, err_d,
+                                                                                    next_masks_d, h->d_cards, h->d_wt, gpw);
   LAUNCH_CHECK();
   return 0;
 }
