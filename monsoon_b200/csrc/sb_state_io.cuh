@@ -216,6 +216,11 @@ SBD_FI int card_strength_of(const G& g, const CardRec& c) {
   return CARD(g, c.card).strength;
 }
 SBD_FI double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
+// k / 5.0 for k = 1..5 (row distance weights, evo/features.py): the correctly rounded quotients as constants instead of
+// one FP64 division per entity on the board
+SBD_FI double fifths(int k) {
+  return k == 1 ? 1.0 / 5.0 : k == 2 ? 2.0 / 5.0 : k == 3 ? 3.0 / 5.0 : k == 4 ? 4.0 / 5.0 : 1.0;
+}
 // returns 0 or SB_ERR_OBS_ID (int(card) raises for UP01-03 anywhere on board, in hand, deck or history: Q12)
 SBD_NI int features(const G& g, double* f) {
   G_LOCAL(g);
@@ -246,18 +251,18 @@ SBD_NI int features(const G& g, double* f) {
     const bool counted = e.strength != -1;
     if (ent_owner(e) == lo) {
       if (!ent_struct(e)) { nl++; if (y < minl) minl = y; } else nsl++;
-      if (counted) { sl += e.strength; prot = __dadd_rn(prot, __dmul_rn((double)e.strength, ddiv((double)(5 - y), 5.0))); }
+      if (counted) { sl += e.strength; prot = __dadd_rn(prot, __dmul_rn((double)e.strength, fifths(5 - y))); }
     } else {
       if (!ent_struct(e)) {
         nr++; if (y > maxr) maxr = y;
-        if (counted) threat = __dadd_rn(threat, __dmul_rn((double)e.strength, ddiv((double)(y + 1), 5.0)));
+        if (counted) threat = __dadd_rn(threat, __dmul_rn((double)e.strength, fifths(y + 1)));
       } else nsr++;
       if (counted) sr += e.strength;
     }
   }
   long long tot = sl + sr;
   f[2] = tot == 0 ? 0.0 : ddiv((double)(sl - sr), (double)tot);
-  f[3] = (nl == 0 && nr == 0) ? 0.0 : ddiv((double)((nr ? maxr : 0) - (nl ? minl : 4)), 4.0);
+  f[3] = (nl == 0 && nr == 0) ? 0.0 : __dmul_rn((double)((nr ? maxr : 0) - (nl ? minl : 4)), 0.25);  // /4: exact scaling
   f[4] = (double)(sl - sr);
   f[5] = (double)(nl - nr);
   f[6] = (double)(nsl - nsr);
@@ -283,7 +288,7 @@ SBD_NI int features(const G& g, double* f) {
   else {
     double playability = ddiv((double)playable, (double)valid);
     double avg = ddiv(total, (double)valid);
-    f[9] = ddiv(__dadd_rn(playability, clip01(ddiv(avg, 3.0))), 2.0);
+    f[9] = __dmul_rn(__dadd_rn(playability, clip01(ddiv(avg, 3.0))), 0.5);  // /2: exact scaling
   }
   #pragma unroll 1
   for (int i = 0; i < L.n_deck; i++) if (CARD(g, L.deck[i].card).obs_id == -32768) err = SB_ERR_OBS_ID;
