@@ -712,11 +712,12 @@ SBD_NI void player_draw(G& g, int order, int amount) {  // player.py:46-52 + num
     {
       double acc = 0.0;
       #pragma unroll 1
-      for (int i = 0; i < n; i++) {
+      for (int i = 0; i < n; i++) {  // the partial sums only grow (weights >= 1): stop at the first one safely above u
         acc += wv[i] * inv;
         const double d = acc - u;
+        if (d > 1e-13) break;
         idx += d < -1e-13;
-        close_call |= (d >= -1e-13) & (d <= 1e-13);
+        close_call |= d >= -1e-13;
       }
     }
 #ifdef SB_FORCE_EXACT_DRAW  // test builds: always take the exact path
