@@ -116,6 +116,8 @@ int sb_rollout_random(SbHandle *h, int n, uint8_t *states_d, int max_steps, int3
 /* FitnessEvaluator._play_game (evo/fitness.py:178-228) with the intended loop (until have_winner or
  * max_steps env steps): FIRST plays w_first_d[idx_first_d[g]], SECOND w_second_d[idx_second_d[g]]
  * (idx arrays nullable = row g... row 0 when the weight table has one row is expressed by idx).
+ * A NULL weight table hands that seat to Stormbound.expert_action (games/stormbound.py:563-637): the agent-vs-expert
+ * match of play_vs_expert.py:65-94, batched.
  * result_d i8[n]: 0 FIRST won, 1 SECOND won, -1 draw/timeout, -2 aborted by an engine exception. */
 int sb_rollout_heuristic(SbHandle *h, int n, uint8_t *states_d, const double *w_first_d, const double *w_second_d,
                          const int32_t *idx_first_d, const int32_t *idx_second_d, int max_steps, int8_t *result_d,

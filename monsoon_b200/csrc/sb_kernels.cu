@@ -505,9 +505,15 @@ __global__ void __launch_bounds__(WPC * 32) k_rollout_heuristic(int n, u8* state
       unpack(g, s);
       copy_g(*base, g);
     }
-    const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
-    const double* ps = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
-    for (int k = 0; k < SB_N_FEATURES; k++) { wf[k] = pf[k]; ws[k] = ps[k]; }
+    // a seat without a weight table is played by the scripted opponent (Stormbound.expert_action)
+    if (w_first) {
+      const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
+      for (int k = 0; k < SB_N_FEATURES; k++) wf[k] = pf[k];
+    }
+    if (w_second) {
+      const double* ps = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
+      for (int k = 0; k < SB_N_FEATURES; k++) ws[k] = ps[k];
+    }
   }
   __syncwarp();
   int k = 0, res = -1;
@@ -516,7 +522,17 @@ __global__ void __launch_bounds__(WPC * 32) k_rollout_heuristic(int n, u8* state
     if (alive && (k >= max_steps || base->pl[0].base < 0 || base->pl[1].base < 0)) alive = false;
     if (BSYNC) { if (!__syncthreads_or(alive)) break; } else if (!alive) break;
     if (alive) {
-      decide(g, base, base->player_sign == 1 ? wf : ws, nullptr, true);
+      const bool first_to_move = base->player_sign == 1;
+      if (first_to_move ? w_first != nullptr : w_second != nullptr) decide(g, base, first_to_move ? wf : ws, nullptr, true);
+      else {  // expert_action draws from the game's own stream, then the action is stepped (games/stormbound.py:563-637)
+        if (lane == 0) {
+          copy_g(g, *base);
+          const int a = expert_action(g);
+          game_step(g, a);
+          base_store(*base, g);
+        }
+        __syncwarp();
+      }
       k++;
       if (base->err) { res = -2; alive = false; }
     }

@@ -204,9 +204,12 @@ class Engine:
         return steps
 
     def rollout_heuristic(self, states, w_first, w_second, idx_first=None, idx_second=None, max_steps=400):
+        """Whole heuristic games; w_first / w_second = None hands that seat to the scripted expert opponent."""
         n = states.shape[0]
-        w_first = self._dev(w_first, torch.float64)
-        w_second = self._dev(w_second, torch.float64)
+        if w_first is None and w_second is None:
+            raise ValueError("at least one seat needs a weight table (expert-vs-expert games: expert_action + step)")
+        w_first = None if w_first is None else self._dev(w_first, torch.float64)
+        w_second = None if w_second is None else self._dev(w_second, torch.float64)
         result = torch.empty(n, dtype=torch.int8, device=self.device)
         steps = torch.empty(n, dtype=torch.int32, device=self.device)
         self._check(self.lib.sb_rollout_heuristic(self.h, n, self._p(states), self._p(w_first), self._p(w_second),

@@ -349,7 +349,19 @@ class FitnessEvaluator:
         per = len(opponents) * g
         return [float(c[0] + 0.5 * c[1]) / per for c in counts]
 
-    def _play(self, population, all_opponents, pairs, g, generation):
+    def evaluate_vs_expert(self, population, generation=0, games=None):
+        """Every individual plays `games` games as FIRST against the scripted opponent Stormbound.expert_action
+        (the agent-vs-expert match of play_vs_expert.py:65-94, batched); returns (wins + 0.5 draws) / games."""
+        n = len(population)
+        g = int(games or self.config.games_per_pairing)
+        start = time.time()
+        counts = self._play(population, list(population), [(i, i) for i in range(n)], g, generation, expert_second=True)
+        self.last_counts = counts
+        self.total_games += n * g
+        self.total_time += time.time() - start
+        return [float(c[0] + 0.5 * c[1]) / g for c in counts]
+
+    def _play(self, population, all_opponents, pairs, g, generation, expert_second=False):
         import torch.distributed as dist
         eng = self._engine()
         dev = eng.device
@@ -378,7 +390,8 @@ class FitnessEvaluator:
                 states = eng.reset(seeds_d, decks, factions)
             else:
                 states = eng.reset(seeds_d)
-            result, _steps = eng.rollout_heuristic(states, w, w, idx_first, idx_second, max_steps=max_steps)
+            result, _steps = eng.rollout_heuristic(states, w, None if expert_second else w, idx_first, None if expert_second else idx_second,
+                                                   max_steps=max_steps)
             eng.accumulate_fitness(result, idx_first, counts)
         if dist_on:
             dist.all_reduce(counts, op=dist.ReduceOp.SUM)  # integer counts: order-independent, bit-exact

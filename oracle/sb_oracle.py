@@ -172,8 +172,8 @@ def select_action(st, w):
 
 
 def play_heuristic(st, w_first, w_second, max_steps=400):
-    wf = np.ascontiguousarray(w_first, dtype=np.float64)
-    ws = np.ascontiguousarray(w_second, dtype=np.float64)
+    wf = None if w_first is None else np.ascontiguousarray(w_first, dtype=np.float64)   # None: that seat plays expert_action
+    ws = None if w_second is None else np.ascontiguousarray(w_second, dtype=np.float64)
     actions = np.zeros(max_steps, dtype=np.uint8)
     n = ctypes.c_int(0)
     r = lib().sbo_play_heuristic(_p(st), _p(wf), _p(ws), max_steps, _p(actions), ctypes.addressof(n))

@@ -202,6 +202,7 @@ int sbo_select_action(const SbState *s, const double *w, double *scores, uint32_
   return best < 0 ? SB_ACTION_PASS : best;
 }
 
+int sbo_expert_action(SbState *s);
 /* Intended loop of evo/fitness.py:193-206 (the is_terminal bug Q15 bypassed): until have_winner or
  * max_steps.  Returns: 0 FIRST wins, 1 SECOND wins, -1 draw/timeout, -2 aborted by an engine exception. */
 int sbo_play_heuristic(SbState *s, const double *w_first, const double *w_second, int max_steps,
@@ -210,7 +211,10 @@ int sbo_play_heuristic(SbState *s, const double *w_first, const double *w_second
   while (k < max_steps) {
     if (s->pl[0].base < 0 || s->pl[1].base < 0) break;
     int to_play = s->player_sign == 1 ? 0 : 1;
-    int a = sbo_select_action(s, to_play == 0 ? w_first : w_second, NULL, NULL);
+    const double *w = to_play == 0 ? w_first : w_second;
+    /* a seat without weights is played by Stormbound.expert_action (games/stormbound.py:563-637; the agent-vs-expert
+     * match of play_vs_expert.py:65-94): it draws from the game's own stream before the step */
+    int a = w ? sbo_select_action(s, w, NULL, NULL) : sbo_expert_action(s);
     sbo_step(s, a);
     if (actions) actions[k] = (uint8_t)a;
     k++;

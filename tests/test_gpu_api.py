@@ -160,3 +160,20 @@ def test_empty_ragged_and_rejected_inputs(engine):
         engine.es_offspring(1, 0, 4, 4, 0.1, 0.01, 1e-5, big, big.clone())  # more than 64 features
     with pytest.raises(_lib.SbError):
         engine.es_select(9, np.zeros(8), big[:, :10].contiguous(), big[:, :10].contiguous())  # mu > rows
+
+
+def test_evaluate_vs_expert_matches_oracle(engine, oracle):
+    from monsoon_b200.evo import FitnessEvaluator, WeightVector, game_seed
+    from monsoon_b200.engine import DEFAULT_DECKS, deck_indices
+    d0, d1 = (deck_indices(d) for d in DEFAULT_DECKS)
+    np.random.seed(12)
+    pop = [WeightVector(10) for _ in range(5)]
+    ev = FitnessEvaluator(Cfg(), engine=engine)
+    fit = ev.evaluate_vs_expert(pop, generation=4, games=3)
+    want = np.zeros(5)
+    for i in range(5):
+        for k in range(3):
+            st = oracle.new_game(game_seed(11, 4, i, i, k), d0, d1, 3, 2)
+            r, _ = oracle.play_heuristic(st, pop[i].weights, None, 400)
+            want[i] += 1.0 if r == 0 else 0.5 if r == -1 else 0.0
+    assert np.allclose(fit, want / 3) and ev.get_stats()["total_games"] == 15

@@ -167,3 +167,21 @@ def test_heuristic_whole_games(engine):
     res, steps = engine.rollout_heuristic(st, torch.from_numpy(z["w_first"]).to(dev), torch.from_numpy(z["w_second"]).to(dev), max_steps=400)
     assert np.array_equal(steps.cpu().numpy(), z["game_lengths"])
     assert np.array_equal(res.cpu().numpy(), z["game_result"])
+
+
+def test_heuristic_vs_expert_games(engine):
+    """sb_rollout_heuristic with one seat handed to the scripted opponent, against the reference's own games
+    (HeuristicAgent vs Stormbound.expert_action, both seatings): winner, length and final state."""
+    z = load("heuristic_vs_expert.npz")
+    dev = engine.device
+    for seat in (0, 1):
+        sel = np.nonzero(z["seat"] == seat)[0]
+        st = engine.reset(torch.from_numpy(z["seeds"][sel].astype(np.int64)).to(dev))
+        w = torch.from_numpy(z["weights"][sel]).to(dev)
+        res, steps = engine.rollout_heuristic(st, w if seat == 0 else None, w if seat == 1 else None, max_steps=400)
+        res, steps, host = res.cpu().numpy(), steps.cpu().numpy(), st.cpu().numpy()
+        assert np.array_equal(res, z["result"][sel])
+        ok = z["result"][sel] != -2
+        assert np.array_equal(steps[ok], z["lengths"][sel][ok])
+        host[:, 19] = 0  # the fixture's final state was packed without the done/reward byte
+        assert np.array_equal(fnv1a64_rows(host[ok]), z["final"][sel][ok])

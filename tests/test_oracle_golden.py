@@ -208,3 +208,24 @@ def test_heuristic_whole_games(oracle):
         off += n
     # a near-tie broken differently by BLAS summation order would fork a game; none is expected at 1e-5
     assert same == len(z["game_seeds"])
+
+
+def test_heuristic_vs_expert_games(oracle):
+    """HeuristicAgent against Stormbound.expert_action (play_vs_expert.py:65-94, intended loop), both seatings:
+    every action, the winner and the final state of the reference's games."""
+    z = load("heuristic_vs_expert.npz")
+    d0, d1 = default_decks()
+    off = 0
+    for i in range(len(z["seeds"])):
+        n, seat = int(z["lengths"][i]), int(z["seat"][i])
+        st = oracle.new_game(int(z["seeds"][i]), d0, d1, 3, 2)
+        w = z["weights"][i]
+        r, acts = oracle.play_heuristic(st, w if seat == 0 else None, w if seat == 1 else None, 400)
+        assert r == int(z["result"][i]), i
+        if r != -2:
+            assert np.array_equal(acts, z["actions"][off:off + n]), i
+            fin = st.copy()
+            fin[19] = 0  # the fixture's final state was packed without the done/reward byte
+            assert oracle.digest(fin) == int(z["final"][i]), i
+        off += n
+
