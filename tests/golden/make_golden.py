@@ -22,6 +22,8 @@ HeuristicAgent), then serialised with pack_reference.  Files:
                         scenarios (plain, sigma reset, diversity injection) x 4 generations
   ref_population.pkl    a checkpoint written by the reference's Population.save_population
   ref_training_log.csv  two rows written by the reference's EvolutionEngine._save_generation_log
+  heuristic_games.npz   BASELINE config 1 at scale: 1,024 whole reference games HeuristicAgent vs HeuristicAgent (seeds 5000.., weights
+                        RandomState(1000+s) / (2000+s)): all actions, winner, final digest
   heuristic_vs_expert.npz  reference games HeuristicAgent vs Stormbound.expert_action (the match of play_vs_expert.py:65-94
                         with the intended loop): 16 games agent FIRST + 16 games agent SECOND, all actions, result, final digest
   expert_tapes.npz      both seats play the reference's Stormbound.expert_action (it draws from the game's stream):
@@ -126,6 +128,39 @@ def work_heur(seed):
     result = 0 if (second.strength < 0 and first.strength >= 0) else 1 if (first.strength < 0 and second.strength >= 0) else -1
     final = h.pack_reference(adapter.game, steps=steps, done=0)
     return seed, w1, w2, np.array(actions, dtype=np.uint8), result, h.fnv1a64(final.tobytes()), samples
+
+
+def work_heur_game(seed):
+    """work_heur without the per-decision samples (whole-game record only)."""
+    import ref_harness as h
+    h.ref()
+    os.chdir(h.REF)
+    from evo.game_adapter import StormboundAdapter
+    from evo.heuristic_agent import HeuristicAgent
+    from evo.weights import WeightVector
+    w1 = np.random.RandomState(1000 + seed).uniform(0, 1, 10)
+    w2 = np.random.RandomState(2000 + seed).uniform(0, 1, 10)
+    wv1, wv2 = WeightVector(10), WeightVector(10)
+    wv1.weights, wv2.weights = w1.copy(), w2.copy()
+    agents = [HeuristicAgent(wv1, 0), HeuristicAgent(wv2, 1)]
+    adapter = StormboundAdapter(h.make_game(seed))
+    actions, steps, err = [], 0, 0
+    with h.quiet():
+        while not adapter.game.env.have_winner() and steps < 400:
+            try:
+                a = agents[adapter.get_current_player()].select_action(adapter)
+                adapter = adapter.apply_action(a)
+            except Exception:  # noqa: BLE001
+                err = 1
+                break
+            actions.append(a)
+            steps += 1
+    b = adapter.game.env.board
+    first = b.local if int(b.local.order) == 0 else b.remote
+    second = b.remote if int(b.local.order) == 0 else b.local
+    result = -2 if err else 0 if (second.strength < 0 and first.strength >= 0) else 1 if (first.strength < 0 and second.strength >= 0) else -1
+    final = 0 if err else h.fnv1a64(h.pack_reference(adapter.game, steps=steps, done=0).tobytes())
+    return seed, w1, w2, np.array(actions, dtype=np.uint8), result, final
 
 
 def work_hve(job):
@@ -273,10 +308,11 @@ def make_es():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--procs", type=int, default=os.cpu_count())
-    ap.add_argument("--only", default="tapes,chain,rand,heur,expert,decks,es,hve")
+    ap.add_argument("--only", default="tapes,chain,rand,heur,expert,decks,es,hve,heurgames")
     ap.add_argument("--n-chain", type=int, default=10000)
     ap.add_argument("--n-rand", type=int, default=3000)
     ap.add_argument("--n-heur", type=int, default=24)
+    ap.add_argument("--n-heur-games", type=int, default=1024)
     args = ap.parse_args()
     only = set(args.only.split(","))
     pool = mp.Pool(args.procs)
@@ -322,6 +358,14 @@ def main():
                             weights=np.stack([s[1] for s in samples]), masks=np.stack([s[2] for s in samples]),
                             scores=np.stack([s[3] for s in samples]), chosen=np.array([s[4] for s in samples], dtype=np.uint8))
         print("heuristic_decisions.npz games", len(res), "samples", len(samples))
+    if "heurgames" in only:
+        res = pool.map(work_heur_game, range(5000, 5000 + args.n_heur_games), chunksize=2)
+        np.savez_compressed(os.path.join(HERE, "heuristic_games.npz"),
+                            seeds=np.array([r[0] for r in res], dtype=np.uint64), w_first=np.stack([r[1] for r in res]),
+                            w_second=np.stack([r[2] for r in res]), lengths=np.array([len(r[3]) for r in res], dtype=np.int32),
+                            actions=np.concatenate([r[3] for r in res]), result=np.array([r[4] for r in res], dtype=np.int8),
+                            final=np.array([r[5] for r in res], dtype=np.uint64))
+        print("heuristic_games.npz", len(res), "aborted", sum(1 for r in res if r[4] == -2))
     if "hve" in only:
         res = pool.map(work_hve, [(400 + i, i % 2) for i in range(32)], chunksize=1)
         np.savez_compressed(os.path.join(HERE, "heuristic_vs_expert.npz"),

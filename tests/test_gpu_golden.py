@@ -185,3 +185,18 @@ def test_heuristic_vs_expert_games(engine):
         assert np.array_equal(steps[ok], z["lengths"][sel][ok])
         host[:, 19] = 0  # the fixture's final state was packed without the done/reward byte
         assert np.array_equal(fnv1a64_rows(host[ok]), z["final"][sel][ok])
+
+
+def test_heuristic_games_at_scale(engine):
+    """BASELINE config 1 on the GPU: the 1,024 reference HeuristicAgent-vs-HeuristicAgent games in one launch."""
+    z = load("heuristic_games.npz")
+    dev = engine.device
+    st = engine.reset(torch.from_numpy(z["seeds"].astype(np.int64)).to(dev))
+    res, steps = engine.rollout_heuristic(st, torch.from_numpy(z["w_first"]).to(dev), torch.from_numpy(z["w_second"]).to(dev), max_steps=400)
+    res, steps, host = res.cpu().numpy(), steps.cpu().numpy(), st.cpu().numpy()
+    assert np.array_equal(res, z["result"])
+    ok = z["result"] != -2
+    assert np.array_equal(steps[ok], z["lengths"][ok])
+    host[:, 19] = 0
+    assert np.array_equal(fnv1a64_rows(host[ok]), z["final"][ok])
+

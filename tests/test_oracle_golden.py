@@ -229,3 +229,23 @@ def test_heuristic_vs_expert_games(oracle):
             assert oracle.digest(fin) == int(z["final"][i]), i
         off += n
 
+
+def test_heuristic_games_at_scale(oracle):
+    """BASELINE config 1: 1,024 whole reference games HeuristicAgent vs HeuristicAgent -- every action, winner, final state."""
+    z = load("heuristic_games.npz")
+    d0, d1 = default_decks()
+    off, bad = 0, []
+    for i in range(len(z["seeds"])):
+        n = int(z["lengths"][i])
+        st = oracle.new_game(int(z["seeds"][i]), d0, d1, 3, 2)
+        r, acts = oracle.play_heuristic(st, z["w_first"][i], z["w_second"][i], 400)
+        ok = r == int(z["result"][i])
+        if ok and r != -2:
+            fin = st.copy()
+            fin[19] = 0
+            ok = np.array_equal(acts, z["actions"][off:off + n]) and oracle.digest(fin) == int(z["final"][i])
+        if not ok:
+            bad.append(int(z["seeds"][i]))
+        off += n
+    assert not bad, bad[:10]
+
