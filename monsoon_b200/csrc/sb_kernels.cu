@@ -27,6 +27,9 @@
 #define SB_ABI_VERSION 1
 #define TPB_GAME 64      // threads per CTA for thread-per-game kernels
 #define WARPS_PER_CTA 4  // games per CTA for warp-per-game kernels
+#ifndef HEUR_MIN_CTAS
+#define HEUR_MIN_CTAS 16  // 4-warp CTAs per SM the heuristic rollout is compiled for (12 -> 42 registers, 1,536 threads/SM)
+#endif
 
 // ---------------------------------------------------------------- helpers
 SBD_FI void stage_cards(DCard* s_cards, const DCard* cards) {
@@ -253,8 +256,8 @@ SBD_FI int pick_action(const G& g) {
 // TPB / BSYNC: with BSYNC the two phases are separated by CTA-wide votes (__syncthreads_or) instead of
 // warp votes, so all TPB/32 warps of a CTA walk the PASS pipeline at the same time and share the
 // instruction-cache lines they fetch (the saturated kernel is instruction-fetch bound).
-template <bool DIGEST, int TPB, bool BSYNC>
-__global__ void __launch_bounds__(TPB) k_rollout_random(int n, u8* states, int max_steps, int* steps_out,
+template <bool DIGEST, int TPB, bool BSYNC, int MINB = 1>
+__global__ void __launch_bounds__(TPB, MINB) k_rollout_random(int n, u8* states, int max_steps, int* steps_out,
                                                         unsigned long long* chain, const DCard* cards, const double* wt,
                                                         int gpw, int turn_sync, int* queue) {
   __shared__ DCard s_cards[SBC_COUNT];
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select_action(int n, con
 // WPC warps (games) per CTA.  BSYNC: all warps of the CTA take their decisions in step (CTA-wide vote per
 // decision), so they walk fork/step/features at the same time and share instruction-cache lines.
 template <int WPC, bool BSYNC>
-__global__ void __launch_bounds__(WPC * 32) k_rollout_heuristic(int n, u8* states, const double* w_first, const double* w_second,
+__global__ void __launch_bounds__(WPC * 32, WPC == 4 ? HEUR_MIN_CTAS : 1) k_rollout_heuristic(int n, u8* states, const double* w_first, const double* w_second,
                                                                 const int* idx_first, const int* idx_second, int max_steps,
                                                                 i8* result, int* steps_out, const DCard* cards, const double* wt) {
   __shared__ DCard s_cards[SBC_COUNT];
@@ -589,6 +592,7 @@ struct SbHandle {
   int ctas_per_sm;
   int refill;      // -1 auto, 0 off, 1 on: finished lanes of the random rollout take the next game from a counter
   int refill_ctas; // persistent CTAs per SM in refill mode (0 = 1024 threads per SM)
+  int dense;       // -1 auto, 0/1: the 32-register variant of the random rollout with two 1,024-thread CTAs per SM
   int refill_grid; // persistent CTAs in total (tests: a grid much smaller than the batch); 0 = sm_count x refill_ctas
   int* d_queue;
   u8* d_pools;    // deck generation: [5][POOL_W] card ids per faction
@@ -622,7 +626,7 @@ static void launch_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max
   int* q = nullptr;
   const int resident = h->sm_count * 1024;  // 64 registers x 1024 threads fill one SM's register file
   int refill = h->refill;
-  if (refill < 0) refill = n >= resident + resident / 4;
+  if (refill < 0) refill = n > resident;  // any batch that does not fit one wave (163,840 games: 258 -> 366 M env-steps/s)
   if (refill && bs >= 128 && h->turn_sync && gpw == 32) {
     q = h->d_queue;
     cudaMemsetAsync(q, 0, sizeof(int), st);
@@ -631,7 +635,14 @@ static void launch_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max
   const int tpb = bs >= 1024 ? 1024 : bs >= 512 ? 512 : bs >= 256 ? 256 : 128;
   const int per_sm = h->refill_ctas > 0 ? h->refill_ctas : 1024 / tpb;
   const int qgrid = h->refill_grid > 0 ? h->refill_grid : h->sm_count * per_sm;
-  if (bs >= 1024 && h->turn_sync)
+  // dense variant: compiled for two 1,024-thread CTAs per SM (32 registers, 2,048 resident lanes per SM); more lanes in
+  // flight hide more of the local-memory latency than the spills cost (tools/sweep_resident.py: 371 -> 400 M at 262 k games)
+  int dense = h->dense;
+  if (dense < 0) dense = n >= h->sm_count * 1536;
+  if (bs >= 1024 && h->turn_sync && q && dense)
+    k_rollout_random<DIGEST, 1024, true, 2><<<h->refill_grid > 0 ? h->refill_grid : 2 * h->sm_count, 1024, 0, st>>>(
+        n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1, q);
+  else if (bs >= 1024 && h->turn_sync)
     k_rollout_random<DIGEST, 1024, true><<<q ? qgrid : grid_for(n, gpw * 32), 1024, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1, q);
   else if (bs >= 512 && h->turn_sync)
     k_rollout_random<DIGEST, 512, true><<<q ? qgrid : grid_for(n, gpw * 16), 512, 0, st>>>(n, states_d, max_steps, steps_d, ch, h->d_cards, h->d_wt, gpw, 1, q);
@@ -730,6 +741,7 @@ int sb_create(int device, SbHandle** out) {
     CK(cudaMalloc(&h->d_arch, 32));
   }
   h->refill = -1;
+  h->dense = -1;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const char* env = getenv("SB_GPW");
   h->gpw = env ? atoi(env) : 0;
@@ -879,6 +891,7 @@ int sb_set_option(SbHandle* h, const char* key, int value) {
   if (!strcmp(key, "games_per_warp")) { h->gpw = value; return 0; }
   if (!strcmp(key, "ctas_per_sm")) { h->ctas_per_sm = value; return 0; }
   if (!strcmp(key, "refill")) { h->refill = value; return 0; }
+  if (!strcmp(key, "dense")) { h->dense = value; return 0; }
   if (!strcmp(key, "refill_ctas")) { h->refill_ctas = value; return 0; }
   if (!strcmp(key, "refill_grid")) { h->refill_grid = value; return 0; }
   return -1;

@@ -37,10 +37,11 @@ def test_10k_default_games_lane_refill(engine):
     ok = z["err"] == 0
     seeds = torch.from_numpy(z["seeds"].astype(np.int64)).to(engine.device)
     try:
-        for bs, grid in ((128, 8), (1024, 2)):
+        for bs, grid, dense in ((128, 8, 0), (1024, 2, 0), (1024, 3, 1)):  # dense = the 32-register, two-CTAs-per-SM variant
             engine.set_option("refill", 1)
             engine.set_option("block_sync", bs)
             engine.set_option("refill_grid", grid)
+            engine.set_option("dense", dense)
             engine.set_option("games_per_warp", 32)
             st = engine.reset(seeds)
             chain = torch.zeros(len(seeds), dtype=torch.int64, device=engine.device)
@@ -50,7 +51,7 @@ def test_10k_default_games_lane_refill(engine):
             assert np.array_equal(chain[ok], z["chain"][ok]), bs
             assert (st.cpu().numpy()[~ok][:, 18] != 0).all()
     finally:
-        for k, v in (("refill", -1), ("block_sync", -1), ("refill_grid", 0), ("games_per_warp", 0)):
+        for k, v in (("refill", -1), ("block_sync", -1), ("refill_grid", 0), ("games_per_warp", 0), ("dense", -1)):
             engine.set_option(k, v)
 
 
