@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(TPB_GAME) k_expert_action(int n, u8* states, u
   out->err = g.err;
 }
 
-__global__ void __launch_bounds__(TPB_GAME) k_step(int n, u8* states, const u8* actions, i8* reward, u8* done, u8* err,
+template <bool DENSE>  // DENSE: compiled for 32 CTAs per SM (32 registers, 2,048 resident threads) for batches that fill the chip
+__global__ void __launch_bounds__(TPB_GAME, DENSE ? 32 : 1) k_step(int n, u8* states, const u8* actions, i8* reward, u8* done, u8* err,
                                                    u32* next_masks, const DCard* cards, const double* wt, int gpw) {
   __shared__ DCard s_cards[SBC_COUNT];
   stage_cards(s_cards, cards);
@@ -713,7 +714,8 @@ int sb_create(int device, SbHandle** out) {
       CK(cudaFuncSetAttribute(k_rollout_random<false, TPB_GAME, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
       CK(cudaFuncSetAttribute(k_rollout_random<true, TPB_GAME, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
       CK(cudaFuncSetAttribute(k_select_action, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-      CK(cudaFuncSetAttribute(k_step, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      CK(cudaFuncSetAttribute(k_step<false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
+      CK(cudaFuncSetAttribute(k_step<true>, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     }
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_rollout_random<false, TPB_GAME, false>, TPB_GAME, 0));
@@ -851,8 +853,14 @@ int sb_step(SbHandle* h, int n, uint8_t* states_d, const uint8_t* actions_d, int
             uint32_t* next_masks_d, void* stream) {
   if (n <= 0) return 0;
   const int gpw = games_per_warp(h, n);
-  k_step<<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, actions_d, (i8*)reward_d, done_d, err_d,
-                                                                                    next_masks_d, h->d_cards, h->d_wt, gpw);
+  int dense = h->dense;
+  if (dense < 0) dense = n >= h->sm_count * 1536;
+  if (dense)
+    k_step<true><<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, actions_d, (i8*)reward_d, done_d, err_d,
+                                                                                            next_masks_d, h->d_cards, h->d_wt, gpw);
+  else
+    k_step<false><<<grid_for(n, gpw * (TPB_GAME / 32)), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, actions_d, (i8*)reward_d, done_d, err_d,
+                                                                                             next_masks_d, h->d_cards, h->d_wt, gpw);
   LAUNCH_CHECK();
   return 0;
 }

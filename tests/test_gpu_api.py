@@ -177,3 +177,24 @@ def test_evaluate_vs_expert_matches_oracle(engine, oracle):
             r, _ = oracle.play_heuristic(st, pop[i].weights, None, 400)
             want[i] += 1.0 if r == 0 else 0.5 if r == -1 else 0.0
     assert np.allclose(fit, want / 3) and ev.get_stats()["total_games"] == 15
+
+
+def test_dense_variants_give_identical_states(engine):
+    """The 32-register (2,048 resident threads per SM) builds of k_step are normally chosen for batches that fill the
+    chip; forced here on a small batch they must produce the same records as the default build."""
+    dev = engine.device
+    seeds = torch.arange(300, dtype=torch.int64, device=dev) + 4242
+    outs = []
+    try:
+        for dense in (0, 1):
+            engine.set_option("dense", dense)
+            st = engine.reset(seeds)
+            engine.rollout_random(st, 15)
+            for _ in range(6):
+                masks = engine.legal_mask(st).cpu().numpy().view(np.uint32)
+                acts = np.array([next(a for a in range(156) if m[a >> 5] >> (a & 31) & 1) for m in masks], dtype=np.uint8)
+                engine.step(st, torch.from_numpy(acts).to(dev))
+            outs.append(st.cpu().numpy())
+    finally:
+        engine.set_option("dense", -1)
+    assert np.array_equal(outs[0], outs[1])
