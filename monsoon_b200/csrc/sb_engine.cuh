@@ -98,6 +98,7 @@ struct G {
   u8 hist_n, hist_card[4], hist_owner[4];
   u8 n_ent, n_trig, resolving, depth, n_mem;
   u8 n_obj;   // card records that are board instances of B305 (SB_CF_OBJ); 0 on the fast path
+  u8 maybe_badobs;  // 0 = no card of this game has an unencodable observation id (UP01-03, Q12): features() skips those scans
   u32 occ;    // occupied-tile bitmask, mirrors board[]
   u32 own1;   // occupied tiles whose entity belongs to order 1 (bits of empty tiles are don't-care)
   u32 strc;   // occupied tiles holding a structure (bits of empty tiles are don't-care)

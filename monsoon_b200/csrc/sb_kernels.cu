@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(TPB_GAME) k_features(int n, const u8* states, 
   __align__(16) SbState s;  // 128-bit moves
   load_state(s, states + (size_t)i * SB_STATE_BYTES);
   unpack(g, s);
+  scan_badobs(g);
   double f[SB_N_FEATURES];
   int e = features(g, f);
   for (int k = 0; k < SB_N_FEATURES; k++) feat[(size_t)i * SB_N_FEATURES + k] = f[k];
@@ -402,7 +403,7 @@ SBD_NI void copy_g(G& dst, const G& src) {
   #pragma unroll 1
   for (int i = 0; i < nm; i++) d8[m0 + i] = s8[m0 + i];
 }
-SBD_FI void base_load(G& g, const SbState& b) { unpack(g, b); }
+SBD_FI void base_load(G& g, const SbState& b) { unpack(g, b); scan_badobs(g); }
 SBD_FI void base_store(SbState& b, G& g) { pack(g, b); }
 SBD_FI void base_load(G& g, const G& b) { copy_g(g, b); }
 SBD_FI void base_store(G& b, G& g) { end_of_step(g); copy_g(b, g); }  // same lazy compaction / overflow rules as the random rollout
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(WPC * 32, WPC == 4 ? HEUR_MIN_CTAS : 1) k_roll
       __align__(16) SbState s;
       load_state(s, states + (size_t)gi * SB_STATE_BYTES);
       unpack(g, s);
+      scan_badobs(g);
       copy_g(*base, g);
     }
     // a seat without a weight table is played by the scripted opponent (Stormbound.expert_action)

@@ -26,6 +26,7 @@ SBD_NI void unpack(G& g, const SbState& s) {
 #pragma unroll
   for (int i = 0; i < 4; i++) { g.hist_card[i] = s.hist_card[i]; g.hist_owner[i] = s.hist_owner[i]; }
   g.n_ent = 0; g.n_trig = 0; g.resolving = 0; g.depth = 0; g.n_mem = 0; g.n_obj = 0; g.occ = 0; g.own1 = 0; g.strc = 0;
+  g.maybe_badobs = 1;  // conservative until scan_badobs() has looked
   #pragma unroll 1
   for (int o = 0; o < 2; o++) {
     const SbPlayer& sp = s.pl[o];
@@ -221,6 +222,28 @@ SBD_FI double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
 SBD_FI double fifths(int k) {
   return k == 1 ? 1.0 / 5.0 : k == 2 ? 2.0 / 5.0 : k == 3 ? 3.0 / 5.0 : k == 4 ? 4.0 / 5.0 : 1.0;
 }
+// The card ids of a game are a closed set (every card in play descends from the two decks; copies keep the id), so
+// one look at everything a freshly unpacked state holds tells whether ANY later state can contain a card without an
+// observation id.  Almost always none can, and features() skips its per-call id scans.
+SBD_NI void scan_badobs(G& g) {
+  G_LOCAL(g);
+  bool any = false;
+  #pragma unroll 1
+  for (int o = 0; o < 2; o++) {
+    const Ply& p = g.pl[o];
+    #pragma unroll 1
+    for (int i = 0; i < p.n_hand; i++) any |= CARD(g, p.hand[i].card).obs_id == -32768;
+    #pragma unroll 1
+    for (int i = 0; i < p.n_deck; i++) any |= CARD(g, p.deck[i].card).obs_id == -32768;
+  }
+  #pragma unroll 1
+  for (int i = 0; i < g.n_ent; i++) any |= CARD(g, g.e[i].card).obs_id == -32768;
+  #pragma unroll 1
+  for (int i = 0; i < g.n_mem; i++) any |= CARD(g, g.mem[i].card).obs_id == -32768;
+  #pragma unroll 1
+  for (int i = 0; i < g.hist_n; i++) any |= CARD(g, g.hist_card[i]).obs_id == -32768;
+  g.maybe_badobs = any ? 1 : 0;
+}
 // returns 0 or SB_ERR_OBS_ID (int(card) raises for UP01-03 anywhere on board, in hand, deck or history: Q12)
 SBD_NI int features(const G& g, double* f) {
   G_LOCAL(g);
@@ -240,13 +263,15 @@ SBD_NI int features(const G& g, double* f) {
   long long sl = 0, sr = 0;
   int nl = 0, nr = 0, nsl = 0, nsr = 0, minl = 99, maxr = -1;
   double threat = 0.0, prot = 0.0;
+  const bool check_ids = g.maybe_badobs != 0;
+  u32 occ = g.occ;
   #pragma unroll 1
-  for (int t = 0; t < SB_N_TILES; t++) {
-    int id = g.board[t];
-    if (id < 0) continue;
-    const Ent& e = g.e[id];
+  while (occ) {  // occupied tiles in ascending order (the accumulation order of the reference's plane scan)
+    const int t = __ffs(occ) - 1;
+    occ &= occ - 1;
+    const Ent& e = g.e[g.board[t]];
     const int y = t >> 2;
-    if (CARD(g, e.card).obs_id == -32768) err = SB_ERR_OBS_ID;
+    if (check_ids && CARD(g, e.card).obs_id == -32768) err = SB_ERR_OBS_ID;
     // the observation uses -1 as "empty": an entity whose strength is exactly -1 would vanish; strengths are >= 0
     const bool counted = e.strength != -1;
     if (ent_owner(e) == lo) {
@@ -290,10 +315,12 @@ SBD_NI int features(const G& g, double* f) {
     double avg = ddiv(total, (double)valid);
     f[9] = __dmul_rn(__dadd_rn(playability, clip01(ddiv(avg, 3.0))), 0.5);  // /2: exact scaling
   }
-  #pragma unroll 1
-  for (int i = 0; i < L.n_deck; i++) if (CARD(g, L.deck[i].card).obs_id == -32768) err = SB_ERR_OBS_ID;
-  #pragma unroll 1
-  for (int i = 0; i < g.hist_n; i++) if (CARD(g, g.hist_card[i]).obs_id == -32768) err = SB_ERR_OBS_ID;
+  if (check_ids) {
+    #pragma unroll 1
+    for (int i = 0; i < L.n_deck; i++) if (CARD(g, L.deck[i].card).obs_id == -32768) err = SB_ERR_OBS_ID;
+    #pragma unroll 1
+    for (int i = 0; i < g.hist_n; i++) if (CARD(g, g.hist_card[i]).obs_id == -32768) err = SB_ERR_OBS_ID;
+  }
   return err;
 }
 

@@ -166,3 +166,48 @@ def test_heuristic_rollout(engine, oracle):
         r, acts = oracle.play_heuristic(host[i], wf[i], ws[i], 400)
         assert (r, len(acts)) == (int(result[i]), int(steps[i])), i
         assert host[i].tobytes() == got[i].tobytes(), i
+
+
+def test_features_and_decisions_with_unencodable_cards(engine, oracle):
+    """UP01-03 have no observation id: `int(card)` raises in the reference as soon as one is on the board, in the
+    mover's hand or deck, or in the play history.  The engine reports SB_ERR_OBS_ID for exactly those
+    states (features, observation) and scores such candidates 0.0; games without these cards skip the id scans."""
+    names = {c["name"]: i for i, c in enumerate(CARDS)}
+    ups = [names["UP01"], names["UP02"], names["UP03"]]
+    n = 96
+    decks, factions = [], []
+    for s in range(n):
+        d, f = random_decks(900 + s, exclude=("UP01", "UP02", "UP03", "S203"))
+        if s % 3 != 2:  # two thirds of the games carry one or two of the cards, in either deck
+            d[s % 2][s % 12] = ups[s % 3]
+            if s % 5 == 0:
+                d[1 - s % 2][(s + 4) % 12] = ups[(s + 1) % 3]
+        decks.append(d)
+        factions.append(f)
+    dev = engine.device
+    seeds = torch.arange(n, dtype=torch.int64, device=dev) + 31000
+    st = engine.reset(seeds, torch.tensor(decks, dtype=torch.uint8, device=dev), torch.tensor(factions, dtype=torch.uint8, device=dev))
+    flagged = 0
+    for depth in (0, 3, 9):
+        if depth:
+            engine.rollout_random(st, 3 if depth == 3 else 6)
+        host = st.cpu().numpy()
+        feat, ferr = engine.features(st)
+        obs, oerr = engine.observe(st)
+        w = torch.from_numpy(np.random.RandomState(depth).uniform(0, 1, (n, 10))).to(dev)
+        acts, scores = engine.select_action(st, w, want_scores=True)
+        feat, ferr, oerr, acts, scores = feat.cpu().numpy(), ferr.cpu().numpy(), oerr.cpu().numpy(), acts.cpu().numpy(), scores.cpu().numpy()
+        for i in range(n):
+            if host[i][18] or host[i][19] & 1:
+                continue
+            o_f, e2 = oracle.features(host[i])
+            _o, e1 = oracle.observe(host[i])
+            assert e2 == int(ferr[i]) and e1 == int(oerr[i]), (depth, i)
+            flagged += e2 != 0
+            if not e2:
+                assert np.array_equal(o_f, feat[i]), (depth, i)
+            a, sc, _m = oracle.select_action(host[i], w[i].cpu().numpy())
+            assert a == int(acts[i]), (depth, i)
+            legal = ~np.isnan(sc)
+            assert np.array_equal(legal, ~np.isnan(scores[i])) and np.allclose(sc[legal], scores[i][legal], rtol=1e-5, atol=0), (depth, i)
+    assert flagged >= 20  # the error path really was exercised
