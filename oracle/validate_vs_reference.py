@@ -95,8 +95,23 @@ def main():
     ap.add_argument("--random-decks", action="store_true")
     ap.add_argument("--exclude", default="UP01,UP02,UP03")
     ap.add_argument("--max-steps", type=int, default=400)
+    ap.add_argument("--what", default="random", choices=["random", "expert", "decks", "es"],
+                    help="random: uniform-agent tapes (rows a1-a10); expert: f3; decks: f2; es: f1")
     args = ap.parse_args()
     lo, hi = (int(x) for x in args.seeds.split(":"))
+    if args.what == "es":
+        ok = all(check_es(seed=sd, scenario=sc) for sd in range(lo, hi) for sc in ("normal", "reset", "inject"))
+        return 0 if ok else 1
+    if args.what == "decks":
+        return 0 if check_decks(lo, hi) else 1
+    if args.what == "expert":
+        bad = 0
+        for seed in range(lo, hi):
+            decks, factions = random_decks(seed, tuple(args.exclude.split(","))) if args.random_decks else (None, None)
+            good, _n, _t = check_expert_seed(seed, decks, factions, args.max_steps)
+            bad += not good
+        print("expert games %d:%d bad=%d" % (lo, hi, bad))
+        return 1 if bad else 0
     ok = bad = steps = errs = unsup = 0
     t0 = time.time()
     for seed in range(lo, hi):
@@ -117,10 +132,6 @@ def main():
     print("seeds %d:%d ok=%d bad=%d steps=%d ref_exceptions_or_overflow=%d unsupported=%d  %.1fs" % (
         lo, hi, ok, bad, steps, errs, unsup, time.time() - t0))
     return 1 if bad else 0
-
-
-if __name__ == "__main__":
-    sys.exit(main())
 
 
 def check_expert_seed(seed, decks=None, factions=None, max_steps=400):
@@ -226,4 +237,33 @@ def check_es(seed=5, generations=6, mu=12, lam=20, scenario="normal"):
         w, s = nw.copy(), ns.copy()  # continue from the reference's state
     print("check_es", scenario, "generations", generations, "events", sorted(seen), "max deviation %.3g" % worst)
     return worst < 1e-12
+
+
+def check_decks(lo, hi):
+    """generate_random_deck / DeckEvolutionConfig of the reference (utils.py) drawing from the injected per-game stream
+    against sbo_generate_decks, three schedules x every generation x seeds lo..hi."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from monsoon_b200.evo import DeckEvolutionConfig as Mirror
+    r = h.ref()
+    import utils
+    bad = tot = 0
+    a1, a2 = h.DEFAULT_DECKS
+    for kw in (dict(), dict(exploit_generations=2, explore_generations=13, max_random_ratio=1.0, balance_archetype_ratio=0.4),
+               dict(exploit_generations=0, explore_generations=7, max_random_ratio=0.8)):
+        ref_cfg = utils.DeckEvolutionConfig([getattr(r.cards, n)() for n in a1], [getattr(r.cards, n)() for n in a2], **kw)
+        mir = Mirror(a1, a2, **kw)
+        for gen in range(ref_cfg.exploit_generations + ref_cfg.explore_generations + 3):
+            mode, k, q = mir.phase_parameters(gen)
+            for seed in range(lo, hi):
+                want = h.reference_decks(seed * 7919 + gen, gen, ref_cfg)
+                got = o.generate_decks(seed * 7919 + gen, gen, mode, k, q, [mir.player1_archetype, mir.player2_archetype],
+                                       [mir.player1_faction, mir.player2_faction])
+                tot += 1
+                bad += got.tolist() != want
+    print("deck pairs %d bad %d" % (tot, bad))
+    return bad == 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
 
