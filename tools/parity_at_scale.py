@@ -1,0 +1,57 @@
+"""GPU box: rollout kernel vs CPU oracle on many more games than the committed fixtures hold: N default-deck and N
+random-deck games (all 112 cards minus UP01-03 / S203), digest chain of every step, step count and final record."""
+import os, sys, random, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+import numpy as np, torch
+import sb_oracle as oracle
+from monsoon_b200.engine import Engine, DEFAULT_DECKS, DEFAULT_FACTIONS, deck_indices
+from monsoon_b200._card_table import CARDS
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+eng = Engine(0); dev = eng.device
+FNV = 0x100000001B3; M64 = (1 << 64) - 1
+
+
+def chain_of(d):
+    c = 0
+    for x in d:
+        c = ((c ^ int(x)) * FNV) & M64
+    return c
+
+
+def rdecks(seed):
+    rng = random.Random(seed); decks = []; f = []
+    for _ in range(2):
+        fa = rng.choice([1, 2, 3, 4])
+        pool = [i for i, c in enumerate(CARDS[:113]) if i > 0 and c["faction"] in (0, fa) and c["name"] not in ("UP01", "UP02", "UP03", "S203")]
+        decks.append(rng.sample(pool, 12)); f.append(fa)
+    return decks, f
+
+
+for label, use_random in (("default decks", False), ("random decks", True)):
+    seeds = np.arange(N, dtype=np.int64) + (700000 if use_random else 400000)
+    if use_random:
+        dd = [rdecks(int(s)) for s in seeds]
+        decks = torch.tensor([d for d, _f in dd], dtype=torch.uint8, device=dev); fac = torch.tensor([f for _d, f in dd], dtype=torch.uint8, device=dev)
+        st = eng.reset(torch.from_numpy(seeds).to(dev), decks, fac)
+    else:
+        d0, d1 = (deck_indices(d) for d in DEFAULT_DECKS)
+        st = eng.reset(torch.from_numpy(seeds).to(dev))
+    chain = torch.zeros(N, dtype=torch.int64, device=dev)
+    steps = eng.rollout_random(st, 400, chain=chain)
+    g_steps, g_chain, g_host = steps.cpu().numpy(), chain.cpu().numpy().view(np.uint64), st.cpu().numpy()
+    bad = flagged = tot = 0
+    t0 = time.time()
+    for i in range(N):
+        if use_random:
+            d, f = dd[i]; s = oracle.new_game(int(seeds[i]), d[0], d[1], f[0], f[1])
+        else:
+            s = oracle.new_game(int(seeds[i]), d0, d1, *DEFAULT_FACTIONS)
+        _a, dig, _m = oracle.rollout_random(s, 400)
+        tot += len(dig)
+        flagged += s[18] != 0
+        if len(dig) != g_steps[i] or chain_of(dig) != int(g_chain[i]) or s.tobytes() != g_host[i].tobytes():
+            bad += 1
+            if bad < 5:
+                print("MISMATCH", label, "seed", int(seeds[i]), len(dig), int(g_steps[i]), int(s[18]), int(g_host[i][18]))
+    print("%s: %d games, %d env steps, %d flagged by both engines, %d mismatches (oracle %.0f s)" % (label, N, tot, flagged, bad, time.time() - t0), flush=True)
