@@ -1,7 +1,9 @@
-"""GPU box: rollout kernel vs CPU oracle on many more games than the committed fixtures hold: N default-deck and N
-random-deck games (all 112 cards minus UP01-03 / S203), digest chain of every step, step count and final record."""
+"""TEST TOOL (GPU box; lives under tests/ because it uses the oracle): rollout kernel vs CPU oracle on many more games
+than the committed fixtures hold -- N default-deck and N random-deck games (all 112 cards minus UP01-03 / S203): digest
+chain of every step, step count and final record.   python tests/parity_at_scale.py 250000
+(tests/test_gpu_scale.py runs the same comparison at a size that fits the GPU test suite.)"""
 import os, sys, random, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root
 sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np, torch
 import sb_oracle as oracle
