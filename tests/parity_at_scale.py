@@ -57,3 +57,25 @@ for label, use_random in (("default decks", False), ("random decks", True)):
             if bad < 5:
                 print("MISMATCH", label, "seed", int(seeds[i]), len(dig), int(g_steps[i]), int(s[18]), int(g_host[i][18]))
     print("%s: %d games, %d env steps, %d flagged by both engines, %d mismatches (oracle %.0f s)" % (label, N, tot, flagged, bad, time.time() - t0), flush=True)
+
+# heuristic agents on both seats (config 1 shape): winner, length and final record of whole games
+NH = min(max(N // 5, 200), 20000)
+seeds = np.arange(NH, dtype=np.int64) + 900000
+w1 = np.random.RandomState(11).uniform(0, 1, (NH, 10))
+w2 = np.random.RandomState(12).uniform(0, 1, (NH, 10))
+d0, d1 = (deck_indices(d) for d in DEFAULT_DECKS)
+st = eng.reset(torch.from_numpy(seeds).to(dev))
+res, steps = eng.rollout_heuristic(st, torch.from_numpy(w1).to(dev), torch.from_numpy(w2).to(dev), max_steps=400)
+g_res, g_steps, g_host = res.cpu().numpy(), steps.cpu().numpy(), st.cpu().numpy()
+bad = tot = 0
+t0 = time.time()
+for i in range(NH):
+    s = oracle.new_game(int(seeds[i]), d0, d1, *DEFAULT_FACTIONS)
+    r, acts = oracle.play_heuristic(s, w1[i], w2[i], 400)
+    tot += len(acts)
+    if r != int(g_res[i]) or len(acts) != int(g_steps[i]) or s.tobytes() != g_host[i].tobytes():
+        bad += 1
+        if bad < 5:
+            print("MISMATCH heuristic seed", int(seeds[i]), r, int(g_res[i]), len(acts), int(g_steps[i]))
+print("heuristic agents: %d games, %d env steps, %d mismatches (oracle %.0f s)" % (NH, tot, bad, time.time() - t0), flush=True)
+
