@@ -37,8 +37,8 @@ int sb_sm_count(SbHandle *h);
  * 1..32 consecutive lanes of every warp that carry a game; "turn_sync" 0/1; "block_sync" = -1 auto, 0, or the
  * CTA size (128..1024) whose warps change phase together; "refill" = -1 auto, 0/1: finished lanes of the random
  * rollout take the next game from a counter ("refill_ctas" persistent CTAs per SM, "refill_grid" CTAs in total,
- * 0 = auto; "dense" = -1 auto, 0/1: 32-register variant with 2,048 resident lanes per SM); "heur_wpc" = warps per CTA of the heuristic rollout;
- * "lanes_per_game" is accepted and ignored (retired shape). */
+ * 0 = auto); "dense" = -1 auto, 0/1: the 32-register builds with 2,048 resident lanes per SM (random rollout, k_step);
+ * "heur_wpc" = warps per CTA of the heuristic rollout; "lanes_per_game" is accepted and ignored (retired shape). */
 int sb_set_option(SbHandle *h, const char *key, int value);
 /* kernels launched through this handle so far (bench.py's gpu_launches) */
 uint64_t sb_launch_count(SbHandle *h);

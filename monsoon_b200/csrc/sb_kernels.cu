@@ -7,10 +7,12 @@
 //   k_expert_action    one game per thread: the scripted opponent (games/stormbound.py:563-637)
 //   k_step             one game per thread: unpack, Stormbound.step, pack, fused next legal mask
 //   k_observe/k_features  one game per thread
-//   k_rollout_random   one game per thread, whole rollout in one launch (state never leaves the SM)
+//   k_rollout_random   one game per thread, whole rollout in one launch (state never leaves the SM); turn-synchronous
+//                      phases, persistent grid with lane refill and a 32-register dense build for large batches
 //   k_select_action    one WARP per game, one lane per candidate action (fork, step, features, score,
 //                      warp arg-max by shuffles) -- evo/heuristic_agent.py:53-80
-//   k_rollout_heuristic  one warp per game, whole game in one launch, base state staged in shared memory
+//   k_rollout_heuristic  one warp per game, whole game in one launch, working-set image of the game in shared memory;
+//                      a seat without weights is played by the scripted opponent
 //   k_accumulate_fitness win/draw/loss counts per individual (evo/fitness.py:95,160-166)
 //   k_es_*             evolution-strategy operators on the resident population (sb_es.cuh; evo/weights.py, evo/population.py)
 // State is AoS [n][512 B]; every thread (or warp) moves its record with 128-bit loads/stores; the card
