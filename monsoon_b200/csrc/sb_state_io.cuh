@@ -311,8 +311,10 @@ SBD_NI int features(const G& g, double* f) {
   }
   if (valid == 0) f[9] = 0.0;
   else {
-    double playability = ddiv((double)playable, (double)valid);
-    double avg = ddiv(total, (double)valid);
+    // valid is 1..4: divisions by 1, 2 and 4 are exact scalings, only /3 needs the divider
+    double playability, avg;
+    if (valid == 3) { playability = ddiv((double)playable, 3.0); avg = ddiv(total, 3.0); }
+    else { const double inv = valid == 1 ? 1.0 : valid == 2 ? 0.5 : 0.25; playability = __dmul_rn((double)playable, inv); avg = __dmul_rn(total, inv); }
     f[9] = __dmul_rn(__dadd_rn(playability, clip01(ddiv(avg, 3.0))), 0.5);  // /2: exact scaling
   }
   if (check_ids) {
