@@ -75,7 +75,16 @@ class OracleEngine:
 
     def reset(self, seeds, decks=None, factions=None):
         import torch
-        return torch.from_numpy(np.stack([self.o.new_game(int(s), self.d[0], self.d[1], 3, 2) for s in seeds.tolist()]))
+        if decks is None:
+            return torch.from_numpy(np.stack([self.o.new_game(int(s), self.d[0], self.d[1], 3, 2) for s in seeds.tolist()]))
+        d, f = decks.numpy(), factions.numpy()
+        return torch.from_numpy(np.stack([self.o.new_game(int(s), d[i][0], d[i][1], int(f[i][0]), int(f[i][1]))
+                                          for i, s in enumerate(seeds.tolist())]))
+
+    def generate_decks(self, seeds, generation, mode, n_preserve=0, q=0.0, archetypes=None, arch_factions=None, factions=None):
+        import torch
+        d = np.stack([self.o.generate_decks(int(s), generation, mode, n_preserve, q, archetypes, arch_factions) for s in seeds.tolist()])
+        return torch.from_numpy(d), torch.from_numpy(np.tile(np.asarray(arch_factions, dtype=np.uint8), (len(d), 1)))
 
     def rollout_heuristic(self, states, w_first, w_second, idx_first, idx_second, max_steps=400):
         import torch
@@ -88,6 +97,13 @@ class OracleEngine:
         for r, i in zip(result.tolist(), idx_first.tolist()):
             counts[i, 0 if r == 0 else 2 if r == 1 else 1] += 1
         return counts
+
+
+def _deck_schedule():
+    from monsoon_b200.evo import DeckEvolutionConfig
+    from monsoon_b200.engine import DEFAULT_DECKS
+    return DeckEvolutionConfig(DEFAULT_DECKS[0], DEFAULT_DECKS[1], exploit_generations=0, explore_generations=2, max_random_ratio=1.0,
+                               balance_archetype_ratio=0.5)
 
 
 def _rank_main(rank, world, port, q):
@@ -103,7 +119,9 @@ def _rank_main(rank, world, port, q):
             v.weights = np.zeros(10)
     ev = FitnessEvaluator(Cfg(), engine=OracleEngine(), chunk_games=5)
     fit = ev.evaluate_population(pop, 0)
-    q.put((rank, fit, ev.last_counts.tolist()))
+    ev2 = FitnessEvaluator(Cfg(), deck_config=_deck_schedule(), engine=OracleEngine(), chunk_games=7)  # per-game decks, balance phase
+    fit2 = ev2.evaluate_population(pop, 5)
+    q.put((rank, fit, ev.last_counts.tolist(), fit2, ev2.last_counts.tolist()))
     dist.destroy_process_group()
 
 
@@ -116,6 +134,8 @@ def test_two_rank_gloo_matches_single_rank():
     single = FitnessEvaluator(Cfg(), engine=OracleEngine(), chunk_games=1000)
     want = single.evaluate_population(pop, 0)
     assert single.last_counts.sum() == 3 * 2 * 3
+    single2 = FitnessEvaluator(Cfg(), deck_config=_deck_schedule(), engine=OracleEngine(), chunk_games=1000)
+    want2 = single2.evaluate_population(pop, 5)
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -128,8 +148,9 @@ def test_two_rank_gloo_matches_single_rank():
     got = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(60)
-    for _rank, fit, counts in got:
+    for _rank, fit, counts, fit2, counts2 in got:
         assert fit == want and counts == single.last_counts.tolist()
+        assert fit2 == want2 and counts2 == single2.last_counts.tolist()  # decks derive from the game seed: partition-invariant
 
 
 # ---------------------------------------------------------------- f4: checkpoint / log formats
