@@ -10,6 +10,8 @@ import sb_oracle as oracle
 from monsoon_b200.engine import Engine, DEFAULT_DECKS, DEFAULT_FACTIONS, deck_indices
 from monsoon_b200._card_table import CARDS
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+# SB_SCALE_ALL_CARDS=1: also the cards the reference cannot observe / orders by hash (UP01-03, S203): engine vs oracle only
+EXCLUDE = () if os.environ.get("SB_SCALE_ALL_CARDS") else ("UP01", "UP02", "UP03", "S203")
 eng = Engine(0); dev = eng.device
 FNV = 0x100000001B3; M64 = (1 << 64) - 1
 
@@ -25,7 +27,7 @@ def rdecks(seed):
     rng = random.Random(seed); decks = []; f = []
     for _ in range(2):
         fa = rng.choice([1, 2, 3, 4])
-        pool = [i for i, c in enumerate(CARDS[:113]) if i > 0 and c["faction"] in (0, fa) and c["name"] not in ("UP01", "UP02", "UP03", "S203")]
+        pool = [i for i, c in enumerate(CARDS[:113]) if i > 0 and c["faction"] in (0, fa) and c["name"] not in EXCLUDE]
         decks.append(rng.sample(pool, 12)); f.append(fa)
     return decks, f
 
