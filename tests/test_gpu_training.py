@@ -101,3 +101,28 @@ def test_evolution_engine_loop(engine, tmp_path):
     assert np.array_equal(first, np.array([v.weights for v in ee2.population.individuals]))
     out2 = ee2.run()
     assert out2["best_fitness"] == out["best_fitness"] and np.array_equal(out2["best_weights"].weights, out["best_weights"].weights)
+
+
+def test_population_checkpoint_round_trip(engine, tmp_path):
+    """Population.save_population / load_population (evo/population.py:281-310) through the reference-compatible
+    pickle, and resuming from the reference's own checkpoint file."""
+    from monsoon_b200.training import EvolutionaryConfig, Population
+    cfg = EvolutionaryConfig(mu=6, lambda_=6, seed=3)
+    pop = Population(cfg, engine=engine)
+    pop.initialize_population(10)
+    pop.fitness_scores, pop.generation = [0.6, 0.5, 0.4, 0.3, 0.2, 0.1], 4
+    path = str(tmp_path / "pop.pkl")
+    pop.save_population(path)
+    other = Population(EvolutionaryConfig(mu=2, lambda_=2), engine=engine)
+    other.load_population(path)
+    assert other.generation == 4 and other.fitness_scores == pop.fitness_scores and other.config == cfg
+    assert np.array_equal(np.array([v.weights for v in other.individuals]), np.array([v.weights for v in pop.individuals]))
+    assert np.array_equal(np.array([v.sigmas for v in other.individuals]), np.array([v.sigmas for v in pop.individuals]))
+    children = other.generate_offspring()  # the resumed population is usable: rows for the offspring exist
+    assert len(children) == 6 and len(other) == 6
+    ref = Population(EvolutionaryConfig(), engine=engine)
+    ref.load_population(os.path.join(GOLDEN, "ref_population.pkl"))  # written by the reference
+    assert ref.generation == 5 and ref.config.mu == 12 and len(ref.individuals) == 12
+    assert len(ref.generate_offspring()) == 20
+    best, fit = ref.get_best_individual()
+    assert fit == max(ref.fitness_scores) and best.size == 10
