@@ -235,13 +235,18 @@ def main():
 
     # end to end through the C ABI with HOST buffers (sb_rollout_random_host: H2D seeds/decks, both kernels,
     # D2H final states + step counts, stream sync), wall clock around the call
+    # The step's inputs (seeds) and results (final states, step counts) live in PINNED host memory.
+    seeds_pin = torch.empty(n, dtype=torch.int64, pin_memory=True)
+    states_pin = torch.empty((n, 512), dtype=torch.uint8, pin_memory=True)
+    steps_pin = torch.empty(n, dtype=torch.int32, pin_memory=True)
     seeds_h = np.arange(n, dtype=np.uint64)
+    sh = seeds_pin.numpy().view(np.uint64)
     e2e_steps, e2e_t = 0, 0.0
     for k in range(warmup + args.steps):
-        sh = seeds_h + np.uint64((rank * 1_000_003 + 50_000 + k) * n)
+        sh[:] = seeds_h + np.uint64((rank * 1_000_003 + 50_000 + k) * n)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        _st, steps_h, _ = eng.rollout_random_host(sh, max_steps=400, want_states=True)
+        _st, steps_h, _ = eng.rollout_random_host(sh, max_steps=400, want_states=True, out_states=states_pin.numpy(), out_steps=steps_pin.numpy())
         dt = time.perf_counter() - t0
         if k >= warmup:
             e2e_steps += int(steps_h.sum())

@@ -236,14 +236,17 @@ class Engine:
                     "sb_step_host")
         return reward, done, err, masks
 
-    def rollout_random_host(self, seeds_np, decks_np=None, factions_np=None, max_steps=400, want_states=True, want_chain=False):
+    def rollout_random_host(self, seeds_np, decks_np=None, factions_np=None, max_steps=400, want_states=True, want_chain=False,
+                            out_states=None, out_steps=None):
+        """Host-buffer variant (sb_rollout_random_host).  out_states / out_steps: caller-owned result buffers, e.g. pinned."""
         n = seeds_np.shape[0]
         if decks_np is None:
             decks_np = np.array([deck_indices(d) for d in DEFAULT_DECKS], dtype=np.uint8)
             factions_np = np.array(DEFAULT_FACTIONS, dtype=np.uint8)
         seeds_np = np.ascontiguousarray(seeds_np, dtype=np.uint64)
-        states = np.empty((n, STATE_BYTES), dtype=np.uint8) if want_states else None
-        steps = np.empty(n, dtype=np.int32)
+        states = (out_states if out_states is not None else np.empty((n, STATE_BYTES), dtype=np.uint8)) if want_states else None
+        steps = out_steps if out_steps is not None else np.empty(n, dtype=np.int32)
+        assert steps.dtype == np.int32 and steps.shape == (n,) and (states is None or (states.dtype == np.uint8 and states.shape == (n, STATE_BYTES)))
         chain = np.zeros(n, dtype=np.uint64) if want_chain else None
         self._check(self.lib.sb_rollout_random_host(self.h, n, seeds_np.ctypes.data, decks_np.ctypes.data, decks_np.shape[-1],
                                                     factions_np.ctypes.data, max_steps,
