@@ -321,20 +321,43 @@ class Population:
 class EvolutionEngine:
     """evo/evolution.py:18-276: the generation loop over the device-resident population and the batched evaluator."""
 
-    def __init__(self, config, deck_config=None, engine=None):
+    def __init__(self, config, deck_config=None, engine=None, evaluation="round_robin"):
+        """evaluation: "round_robin" = the reference's schedule (everyone against everyone and the hall of fame,
+        evo/fitness.py:32-118); "vs_hall_of_fame" = every individual plays games_per_pairing games as FIRST against the
+        hall of fame and one fixed baseline vector (BASELINE config 4: work linear in the population)."""
         self.config = config
         self.deck_config = deck_config
         self.eng = engine
+        self.evaluation = evaluation
         self.population = None
         self.fitness_evaluator = None
         self.results_dir = config.results_dir
         self.start_time = None
+        self.baseline = WeightVector.__new__(WeightVector)
+        self.baseline.weights = np.random.RandomState(7).uniform(0, 1, len(FEATURE_NAMES))
+        self.baseline.sigmas, self.baseline.size = np.full(len(FEATURE_NAMES), 0.1), len(FEATURE_NAMES)
 
     def initialize(self):
         os.makedirs(self.results_dir, exist_ok=True)
         self.population = Population(self.config, engine=self.eng)
         self.population.initialize_population(len(FEATURE_NAMES))
         self.fitness_evaluator = FitnessEvaluator(self.config, self.deck_config, engine=self.population.eng)
+
+    def load_checkpoint(self, checkpoint_path):
+        """Resume from a population checkpoint (ours or the reference's, evo/evolution.py:243-254)."""
+        os.makedirs(self.results_dir, exist_ok=True)
+        self.population = Population(self.config, engine=self.eng)
+        self.population.load_population(checkpoint_path)
+        self.config = self.population.config
+        self.fitness_evaluator = FitnessEvaluator(self.config, self.deck_config, engine=self.population.eng)
+
+    def _evaluate(self, everyone, generation):
+        ev = self.fitness_evaluator
+        if self.evaluation == "round_robin":
+            return ev.evaluate_population(everyone, generation)
+        fitness = ev.evaluate_vs(everyone, list(ev.hall_of_fame) + [self.baseline], generation)
+        ev._update_hall_of_fame(everyone, fitness)
+        return fitness
 
     def step(self):
         """One pass of the loop body of evo/evolution.py:77-110; returns the generation wall time."""
@@ -343,7 +366,7 @@ class EvolutionEngine:
         everyone = pop.get_parents()
         if pop.generation > 0:
             everyone = everyone + pop.generate_offspring()
-        fitness = self.fitness_evaluator.evaluate_population(everyone, pop.generation)
+        fitness = self._evaluate(everyone, pop.generation)
         if pop.generation == 0:
             pop.fitness_scores = fitness
             pop.generation += 1

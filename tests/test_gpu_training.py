@@ -126,3 +126,23 @@ def test_population_checkpoint_round_trip(engine, tmp_path):
     assert len(ref.generate_offspring()) == 20
     best, fit = ref.get_best_individual()
     assert fit == max(ref.fitness_scores) and best.size == 10
+
+
+def test_evolution_engine_vs_hall_of_fame_and_resume(engine, tmp_path):
+    """The linear schedule of BASELINE config 4 (hall of fame + baseline opponents) and resuming from a checkpoint."""
+    from monsoon_b200.training import EvolutionaryConfig, EvolutionEngine
+    cfg = EvolutionaryConfig(mu=6, lambda_=6, generations=2, games_per_pairing=2, max_turns=400, seed=9, checkpoint_interval=1,
+                             results_dir=str(tmp_path / "a"))
+    ee = EvolutionEngine(cfg, engine=engine, evaluation="vs_hall_of_fame")
+    ee.initialize()
+    out = ee.run()
+    assert out["final_generation"] == 2 and len(ee.fitness_evaluator.hall_of_fame) == 5
+    assert out["eval_stats"]["total_games"] == 6 * 1 * 2 + 12 * 6 * 2  # generation 0: baseline only; then 5 hall-of-fame + baseline
+    ckpt = sorted(f for f in os.listdir(cfg.results_dir) if f.startswith("checkpoint_gen1_"))[0]
+    cfg2 = EvolutionaryConfig(**dict(cfg.to_dict(), results_dir=str(tmp_path / "b"), generations=3))
+    ee2 = EvolutionEngine(cfg2, engine=engine, evaluation="vs_hall_of_fame")
+    ee2.load_checkpoint(os.path.join(cfg.results_dir, ckpt))
+    assert ee2.population.generation == 1 and ee2.config.generations == 2  # the checkpoint carries its configuration
+    ee2.config.generations = 3
+    out2 = ee2.run()
+    assert out2["final_generation"] == 3
