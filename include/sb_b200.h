@@ -28,6 +28,8 @@ int sb_state_bytes(void);                 /* == SB_STATE_BYTES */
 int sb_card_count(void);                  /* rows of the card table (130) */
 int sb_card_info(int card, int32_t out[12]); /* kind,faction,cost,strength,movement,trigger,fixed,has_ability,first_type,types,obs_id,has_target */
 
+/* One handle per device and per stream of use: the handle owns small device scratch (refill counter, staged archetypes,
+ * host-variant staging buffer), so two calls through the SAME handle must not run concurrently on different streams. */
 int sb_create(int device, SbHandle **out);
 int sb_destroy(SbHandle *h);
 const char *sb_last_error(SbHandle *h);
