@@ -394,13 +394,23 @@ SBD_FI double score_delta(const double* w, const double* fc, const double* fn) {
 SBD_NI void copy_g(G& dst, const G& src) {
   typedef unsigned long long u64;
   static_assert(offsetof(G, board) % 8 == 0 && offsetof(G, trig) % 8 == 0 && sizeof(Ent) % 8 == 0 && sizeof(Mem) % 8 == 0, "copy_g layout");
+  static_assert(offsetof(G, pl) % 8 == 0 && sizeof(Ply) % 8 == 0 && offsetof(Ply, deck) % 8 == 0 && sizeof(CardRec) == 8, "copy_g layout");
   const u64* s8 = reinterpret_cast<const u64*>(&src);
   u64* d8 = reinterpret_cast<u64*>(&dst);
   const int ne = src.n_ent * (int)(sizeof(Ent) / 8);
   #pragma unroll 4
   for (int i = 0; i < ne; i++) d8[i] = s8[i];
-  #pragma unroll 8
-  for (int i = (int)(offsetof(G, board) / 8); i < (int)(offsetof(G, trig) / 8); i++) d8[i] = s8[i];
+  // the block [board .. trig) without the unused tails of the two deck arrays (a deck holds 8-12 of its 20 slots; slots
+  // beyond n_deck are never read before they are written): board + player 0 up to its last deck card, player 1 likewise,
+  // then the scalars behind the players
+  const int p0 = (int)(offsetof(G, pl) / 8), pw = (int)(sizeof(Ply) / 8), dk = (int)(offsetof(Ply, deck) / 8);
+  const int e0 = p0 + dk + src.pl[0].n_deck, e1 = p0 + pw + dk + src.pl[1].n_deck;
+  #pragma unroll 4
+  for (int i = (int)(offsetof(G, board) / 8); i < e0; i++) d8[i] = s8[i];
+  #pragma unroll 4
+  for (int i = p0 + pw; i < e1; i++) d8[i] = s8[i];
+  #pragma unroll
+  for (int i = p0 + 2 * pw; i < (int)(offsetof(G, trig) / 8); i++) d8[i] = s8[i];
   const int m0 = (int)(offsetof(G, mem) / 8), nm = src.n_mem * (int)(sizeof(Mem) / 8);
   #pragma unroll 1
   for (int i = 0; i < nm; i++) d8[m0 + i] = s8[m0 + i];

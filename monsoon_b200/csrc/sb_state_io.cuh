@@ -219,8 +219,17 @@ SBD_FI int card_strength_of(const G& g, const CardRec& c) {
 SBD_FI double clip01(double v) { return v < 0.0 ? 0.0 : (v > 1.0 ? 1.0 : v); }
 // k / 5.0 for k = 1..5 (row distance weights, evo/features.py): the correctly rounded quotients as constants instead of
 // one FP64 division per entity on the board
+// (assembled from the bit patterns with integer selects: the ternary chain on doubles compiled to a jump table, and
+// the lanes of a warp ask for different rows)
 SBD_FI double fifths(int k) {
-  return k == 1 ? 1.0 / 5.0 : k == 2 ? 2.0 / 5.0 : k == 3 ? 3.0 / 5.0 : k == 4 ? 4.0 / 5.0 : 1.0;
+  static_assert(sizeof(double) == 8, "IEEE double");
+  // 1/5 = 0x3FC999999999999A, 2/5 = 0x3FD999999999999A, 3/5 = 0x3FE3333333333333, 4/5 = 0x3FE999999999999A, 1 = 0x3FF0000000000000
+  u32 hi = 0x3FF00000u, lo = 0u;
+  hi = k == 4 ? 0x3FE99999u : hi;  lo = k == 4 ? 0x9999999Au : lo;
+  hi = k == 3 ? 0x3FE33333u : hi;  lo = k == 3 ? 0x33333333u : lo;
+  hi = k == 2 ? 0x3FD99999u : hi;  lo = k == 2 ? 0x9999999Au : lo;
+  hi = k == 1 ? 0x3FC99999u : hi;  lo = k == 1 ? 0x9999999Au : lo;
+  return __hiloint2double((int)hi, (int)lo);
 }
 // The card ids of a game are a closed set (every card in play descends from the two decks; copies keep the id), so
 // one look at everything a freshly unpacked state holds tells whether ANY later state can contain a card without an
@@ -260,7 +269,10 @@ SBD_NI int features(const G& g, double* f) {
   if (est > 10.0) est = 10.0;
   f[0] = clip01(__dsub_rn(1.0, ddiv(m, est)));
   f[1] = __dsub_rn(hl, hr);
-  long long sl = 0, sr = 0;
+  // The tile loop is written without data-dependent branches (selects only): lanes of a warp hold different forks, and
+  // the branchy version cost ~100 warp instructions per tile in the ncu source view (two jump tables for the row
+  // weight, four owner / kind paths), the select form is one straight stream.  Sums of i16 strengths fit an int.
+  int sl = 0, sr = 0;
   int nl = 0, nr = 0, nsl = 0, nsr = 0, minl = 99, maxr = -1;
   double threat = 0.0, prot = 0.0;
   const bool check_ids = g.maybe_badobs != 0;
@@ -272,20 +284,28 @@ SBD_NI int features(const G& g, double* f) {
     const Ent& e = g.e[g.board[t]];
     const int y = t >> 2;
     if (check_ids && CARD(g, e.card).obs_id == -32768) err = SB_ERR_OBS_ID;
+    const int str = e.strength;
+    const u32 fl = e.fl;
     // the observation uses -1 as "empty": an entity whose strength is exactly -1 would vanish; strengths are >= 0
-    const bool counted = e.strength != -1;
-    if (ent_owner(e) == lo) {
-      if (!ent_struct(e)) { nl++; if (y < minl) minl = y; } else nsl++;
-      if (counted) { sl += e.strength; prot = __dadd_rn(prot, __dmul_rn((double)e.strength, fifths(5 - y))); }
-    } else {
-      if (!ent_struct(e)) {
-        nr++; if (y > maxr) maxr = y;
-        if (counted) threat = __dadd_rn(threat, __dmul_rn((double)e.strength, fifths(y + 1)));
-      } else nsr++;
-      if (counted) sr += e.strength;
-    }
+    const bool counted = str != -1;
+    const bool mine = (int)(fl & EF_OWNER) == lo;
+    const bool unit = !(fl & EF_STRUCT);
+    const int cs = counted ? str : 0;
+    nl += (mine && unit) ? 1 : 0;
+    nsl += (mine && !unit) ? 1 : 0;
+    nr += (!mine && unit) ? 1 : 0;
+    nsr += (!mine && !unit) ? 1 : 0;
+    minl = (mine && unit && y < minl) ? y : minl;
+    maxr = (!mine && unit && y > maxr) ? y : maxr;
+    sl += mine ? cs : 0;
+    sr += mine ? 0 : cs;
+    // protection: own entities (units and structures) by closeness to the own base; threat: enemy units by closeness to it
+    const double x = __dmul_rn((double)str, fifths(mine ? 5 - y : y + 1));
+    const double acc = __dadd_rn(mine ? prot : threat, x);
+    prot = (mine && counted) ? acc : prot;
+    threat = (!mine && unit && counted) ? acc : threat;
   }
-  long long tot = sl + sr;
+  const int tot = sl + sr;
   f[2] = tot == 0 ? 0.0 : ddiv((double)(sl - sr), (double)tot);
   f[3] = (nl == 0 && nr == 0) ? 0.0 : __dmul_rn((double)((nr ? maxr : 0) - (nl ? minl : 4)), 0.25);  // /4: exact scaling
   f[4] = (double)(sl - sr);
