@@ -499,76 +499,88 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) k_select_action(int n, con
 
 // WPC warps (games) per CTA.  BSYNC: all warps of the CTA take their decisions in step (CTA-wide vote per
 // decision), so they walk fork/step/features at the same time and share instruction-cache lines.
+// queue != nullptr (independent warps only): persistent grid; a warp whose game is over takes the next game index from
+// a global counter, so a CTA slot never idles while its longest game finishes (games differ 3x in length; ncu showed
+// 72 % active warps with one game per warp and CTA) and CTAs can be large enough to share one card table.
 template <int WPC, bool BSYNC>
-__global__ void __launch_bounds__(WPC * 32, WPC == 4 ? HEUR_MIN_CTAS : 1) k_rollout_heuristic(int n, u8* states, const double* w_first, const double* w_second,
+__global__ void __launch_bounds__(WPC * 32, BSYNC ? 1 : (HEUR_MIN_CTAS * 4) / WPC) k_rollout_heuristic(int n, u8* states, const double* w_first, const double* w_second,
                                                                 const int* idx_first, const int* idx_second, int max_steps,
-                                                                i8* result, int* steps_out, const DCard* cards, const double* wt) {
+                                                                i8* result, int* steps_out, const DCard* cards, const double* wt, int* queue) {
   __shared__ DCard s_cards[SBC_COUNT];
   extern __shared__ __align__(16) unsigned char s_dyn[];  // WPC working-set images (sizeof(G) each)
   G* s_base = reinterpret_cast<G*>(s_dyn);
   stage_cards(s_cards, cards);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gi = blockIdx.x * WPC + warp;
-  const bool has_game = gi < n;
-  if (!BSYNC && !has_game) return;
   G* base = &s_base[warp];
   G g;
   init_g(g, s_cards, wt);
   double wf[SB_N_FEATURES], ws[SB_N_FEATURES];
-  if (has_game) {
-    if (lane == 0) {  // packed record -> working set -> shared image, once per game
-      __align__(16) SbState s;
-      load_state(s, states + (size_t)gi * SB_STATE_BYTES);
-      unpack(g, s);
-      scan_badobs(g);
-      copy_g(*base, g);
-    }
-    // a seat without a weight table is played by the scripted opponent (Stormbound.expert_action)
-    if (w_first) {
-      const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
-      for (int k = 0; k < SB_N_FEATURES; k++) wf[k] = pf[k];
-    }
-    if (w_second) {
-      const double* ps = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
-      for (int k = 0; k < SB_N_FEATURES; k++) ws[k] = ps[k];
-    }
-  }
-  __syncwarp();
-  int k = 0, res = -1;
-  bool alive = has_game;
+  int gi = blockIdx.x * WPC + warp;
+  #pragma unroll 1
   for (;;) {
-    if (alive && (k >= max_steps || base->pl[0].base < 0 || base->pl[1].base < 0)) alive = false;
-    if (BSYNC) { if (!__syncthreads_or(alive)) break; } else if (!alive) break;
-    if (alive) {
-      const bool first_to_move = base->player_sign == 1;
-      if (first_to_move ? w_first != nullptr : w_second != nullptr) decide(g, base, first_to_move ? wf : ws, nullptr, true);
-      else {  // expert_action draws from the game's own stream, then the action is stepped (games/stormbound.py:563-637)
-        if (lane == 0) {
-          copy_g(g, *base);
-          const int a = expert_action(g);
-          game_step(g, a);
-          base_store(*base, g);
-        }
-        __syncwarp();
-      }
-      k++;
-      if (base->err) { res = -2; alive = false; }
+    if (!BSYNC && queue) {
+      if (lane == 0) gi = atomicAdd(queue, 1);
+      gi = __shfl_sync(0xFFFFFFFFu, gi, 0);
     }
-  }
-  if (has_game) {
-    if (res != -2) {
-      bool l0 = base->pl[0].base < 0, l1 = base->pl[1].base < 0;
-      res = (l1 && !l0) ? 0 : (l0 && !l1) ? 1 : -1;
+    const bool has_game = gi < n;
+    if (!BSYNC && !has_game) return;
+    if (has_game) {
+      if (lane == 0) {  // packed record -> working set -> shared image, once per game
+        __align__(16) SbState s;
+        load_state(s, states + (size_t)gi * SB_STATE_BYTES);
+        unpack(g, s);
+        scan_badobs(g);
+        copy_g(*base, g);
+      }
+      // a seat without a weight table is played by the scripted opponent (Stormbound.expert_action)
+      if (w_first) {
+        const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
+        for (int k = 0; k < SB_N_FEATURES; k++) wf[k] = pf[k];
+      }
+      if (w_second) {
+        const double* ps = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
+        for (int k = 0; k < SB_N_FEATURES; k++) ws[k] = ps[k];
+      }
     }
     __syncwarp();
-    if (lane == 0) {
-      __align__(16) SbState s;
-      copy_g(g, *base);
-      pack(g, s);
-      store_state(states + (size_t)gi * SB_STATE_BYTES, s);
-      if (result) result[gi] = (i8)res;
-      if (steps_out) steps_out[gi] = k;
+    int k = 0, res = -1;
+    bool alive = has_game;
+    for (;;) {
+      if (alive && (k >= max_steps || base->pl[0].base < 0 || base->pl[1].base < 0)) alive = false;
+      if (BSYNC) { if (!__syncthreads_or(alive)) break; } else if (!alive) break;
+      if (alive) {
+        const bool first_to_move = base->player_sign == 1;
+        if (first_to_move ? w_first != nullptr : w_second != nullptr) decide(g, base, first_to_move ? wf : ws, nullptr, true);
+        else {  // expert_action draws from the game's own stream, then the action is stepped (games/stormbound.py:563-637)
+          if (lane == 0) {
+            copy_g(g, *base);
+            const int a = expert_action(g);
+            game_step(g, a);
+            base_store(*base, g);
+          }
+          __syncwarp();
+        }
+        k++;
+        if (base->err) { res = -2; alive = false; }
+      }
     }
+    if (has_game) {
+      if (res != -2) {
+        bool l0 = base->pl[0].base < 0, l1 = base->pl[1].base < 0;
+        res = (l1 && !l0) ? 0 : (l0 && !l1) ? 1 : -1;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __align__(16) SbState s;
+        copy_g(g, *base);
+        pack(g, s);
+        store_state(states + (size_t)gi * SB_STATE_BYTES, s);
+        if (result) result[gi] = (i8)res;
+        if (steps_out) steps_out[gi] = k;
+      }
+    }
+    if (BSYNC || !queue) return;
+    __syncwarp();  // the image is free for the next game
   }
 }
 
@@ -609,6 +621,9 @@ struct SbHandle {
   int refill_ctas; // persistent CTAs per SM in refill mode (0 = 1024 threads per SM)
   int dense;       // -1 auto, 0/1: the 32-register variant of the random rollout with two 1,024-thread CTAs per SM
   int refill_grid; // persistent CTAs in total (tests: a grid much smaller than the batch); 0 = sm_count x refill_ctas
+  int heur_iw;     // heuristic rollout, independent warps: warps per CTA (4, 8, 16; -1 = auto)
+  int heur_grid;   // persistent CTAs in refill mode (tests: a grid much smaller than the batch); 0 = one wave
+  int heur_refill; // -1 auto, 0 off, 1 on: a warp whose game ended takes the next game from a counter
   int* d_queue;
   u8* d_pools;    // deck generation: [5][POOL_W] card ids per faction
   int* d_pool_n;
@@ -742,7 +757,9 @@ int sb_create(int device, SbHandle** out) {
   CK(cudaFuncSetAttribute(k_rollout_heuristic<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * sizeof(G))));
   CK(cudaFuncSetAttribute(k_rollout_heuristic<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(G))));
   CK(cudaFuncSetAttribute(k_rollout_heuristic<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(G))));
-  CK(cudaMalloc(&h->d_queue, sizeof(int)));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(G))));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * sizeof(G))));
+  CK(cudaMalloc(&h->d_queue, 2 * sizeof(int)));  // [0] random rollout lanes, [1] heuristic rollout warps
   {  // deck pools: dir(cards) order == card index order; own faction + NEUTRAL (utils.py:74-84)
     static u8 pools[5 * POOL_W];
     int pn[5] = {0, 0, 0, 0, 0};
@@ -758,6 +775,8 @@ int sb_create(int device, SbHandle** out) {
   }
   h->refill = -1;
   h->dense = -1;
+  h->heur_iw = -1;
+  h->heur_refill = -1;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const char* env = getenv("SB_GPW");
   h->gpw = env ? atoi(env) : 0;
@@ -916,6 +935,9 @@ int sb_set_option(SbHandle* h, const char* key, int value) {
   if (!strcmp(key, "dense")) { h->dense = value; return 0; }
   if (!strcmp(key, "refill_ctas")) { h->refill_ctas = value; return 0; }
   if (!strcmp(key, "refill_grid")) { h->refill_grid = value; return 0; }
+  if (!strcmp(key, "heur_iw")) { h->heur_iw = value; return 0; }
+  if (!strcmp(key, "heur_grid")) { h->heur_grid = value; return 0; }
+  if (!strcmp(key, "heur_refill")) { h->heur_refill = value; return 0; }
   return -1;
 }
 int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_first_d, const double* w_second_d,
@@ -926,9 +948,25 @@ int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_
   int hw = h->heur_wpc;
   if (hw < 0) hw = 4;  // auto (tools/sweep_heur.py): with the shared working-set image independent warps win at every batch size;
                        // limiting resident threads to fit L2 only loses (tools/sweep_heur_resident.py, removed knob)
-#define HEUR(W, B) k_rollout_heuristic<W, B><<<grid_for(n, W), W * 32, W * sizeof(G), st>>>(n, states_d, w_first_d, w_second_d, idx_first_d, \
-                                                                                       idx_second_d, max_steps, (i8*)result_d, steps_d, h->d_cards, h->d_wt)
-  if (hw >= 32) HEUR(32, true); else if (hw >= 16) HEUR(16, true); else if (hw >= 8) HEUR(8, true); else HEUR(4, false);
+  // independent warps: iw warps per CTA (4 / 8 / 16); batches beyond one wave run as a persistent grid with warp refill
+  const int wave = h->sm_count * HEUR_MIN_CTAS * 4;  // resident warps = games in flight
+  int refill = h->heur_refill;
+  if (refill < 0) refill = n > wave;  // measured (tools/time_heur.py): 65,536 games 441 -> 404 ms, 399 ms with 8-warp CTAs
+  const int iw_opt = h->heur_iw > 0 ? h->heur_iw : (refill ? 8 : 4);  // refill removes the CTA tail, so CTAs can share more
+  const int iw = iw_opt >= 16 ? 16 : iw_opt >= 8 ? 8 : 4;
+  int* q = nullptr;
+  if (refill && hw < 8) {
+    q = h->d_queue + 1;
+    cudaMemsetAsync(q, 0, sizeof(int), st);
+  }
+#define HEUR(W, B, GRID) k_rollout_heuristic<W, B><<<GRID, W * 32, W * sizeof(G), st>>>(n, states_d, w_first_d, w_second_d, idx_first_d, \
+                                                                                       idx_second_d, max_steps, (i8*)result_d, steps_d, h->d_cards, h->d_wt, q)
+  if (hw >= 32) HEUR(32, true, grid_for(n, 32)); else if (hw >= 16) HEUR(16, true, grid_for(n, 16)); else if (hw >= 8) HEUR(8, true, grid_for(n, 8));
+  else {
+    const int full = grid_for(n, iw), resident = wave / iw;
+    const int grid = q && h->heur_grid > 0 ? h->heur_grid : (q && full > resident ? resident : full);
+    if (iw == 16) HEUR(16, false, grid); else if (iw == 8) HEUR(8, false, grid); else HEUR(4, false, grid);
+  }
 #undef HEUR
   LAUNCH_CHECK();
   return 0;

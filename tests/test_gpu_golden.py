@@ -201,3 +201,46 @@ def test_heuristic_games_at_scale(engine):
     host[:, 19] = 0
     assert np.array_equal(fnv1a64_rows(host[ok]), z["final"][ok])
 
+
+
+@pytest.mark.parametrize("iw,grid", [(4, 6), (8, 5), (16, 3), (8, 0)])
+def test_heuristic_games_with_warp_refill(engine, iw, grid):
+    """The persistent shape of the heuristic rollout (a warp whose game ended takes the next game from a counter) on a grid
+    much smaller than the batch: the same 1,024 reference games, same winners, lengths and final states."""
+    z = load("heuristic_games.npz")
+    dev = engine.device
+    try:
+        engine.set_option("heur_refill", 1)
+        engine.set_option("heur_iw", iw)
+        engine.set_option("heur_grid", grid)
+        st = engine.reset(torch.from_numpy(z["seeds"].astype(np.int64)).to(dev))
+        res, steps = engine.rollout_heuristic(st, torch.from_numpy(z["w_first"]).to(dev), torch.from_numpy(z["w_second"]).to(dev), max_steps=400)
+        res, steps, host = res.cpu().numpy(), steps.cpu().numpy(), st.cpu().numpy()
+    finally:
+        for k, v in (("heur_refill", -1), ("heur_iw", -1), ("heur_grid", 0)):
+            engine.set_option(k, v)
+    assert np.array_equal(res, z["result"])
+    ok = z["result"] != -2
+    assert np.array_equal(steps[ok], z["lengths"][ok])
+    host[:, 19] = 0
+    assert np.array_equal(fnv1a64_rows(host[ok]), z["final"][ok])
+
+
+def test_heuristic_vs_expert_with_warp_refill(engine):
+    """Refill shape with one seat handed to the scripted opponent: identical to the one-wave shape."""
+    dev = engine.device
+    seeds = torch.arange(3000, dtype=torch.int64, device=dev) + 777
+    w = torch.from_numpy(np.random.RandomState(5).uniform(0, 1, (3000, 10))).to(dev)
+    out = []
+    for refill, grid in ((0, 0), (1, 7)):
+        try:
+            engine.set_option("heur_refill", refill)
+            engine.set_option("heur_grid", grid)
+            st = engine.reset(seeds)
+            res, steps = engine.rollout_heuristic(st, w, None, max_steps=400)
+            out.append((res.cpu().numpy(), steps.cpu().numpy(), st.cpu().numpy()))
+        finally:
+            engine.set_option("heur_refill", -1)
+            engine.set_option("heur_grid", 0)
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)

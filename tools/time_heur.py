@@ -9,6 +9,10 @@ if os.environ.get('SB_LIB'):
     _lib.SO_PATH = os.path.abspath(os.environ['SB_LIB'])  # A/B: time another build of the library
 from monsoon_b200.engine import Engine
 eng = Engine(0); dev = eng.device
+for kv in os.environ.get('SB_OPTS', '').split(','):  # e.g. SB_OPTS=heur_iw=8,heur_refill=1
+    if kv:
+        k, v = kv.split('=')
+        assert eng.lib.sb_set_option(eng.h, k.encode(), int(v)) == 0, kv
 sizes = [int(x) for x in (sys.argv[1] if len(sys.argv) > 1 else "4096,16384,65536").split(",")]
 for n in sizes:
     P = 256; GPI = max(n // P, 1)
