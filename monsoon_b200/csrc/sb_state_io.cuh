@@ -269,9 +269,8 @@ SBD_NI int features(const G& g, double* f) {
   if (est > 10.0) est = 10.0;
   f[0] = clip01(__dsub_rn(1.0, ddiv(m, est)));
   f[1] = __dsub_rn(hl, hr);
-  // The tile loop is written without data-dependent branches (selects only): lanes of a warp hold different forks, and
-  // the branchy version cost ~100 warp instructions per tile in the ncu source view (two jump tables for the row
-  // weight, four owner / kind paths), the select form is one straight stream.  Sums of i16 strengths fit an int.
+  // The forks of one decision share most tiles, so the owner / kind branches below are mostly uniform across a warp
+  // (ncu source view: ~53 warp instructions per tile against 83 for a select-only form).  Sums of i16 strengths fit an int.
   int sl = 0, sr = 0;
   int nl = 0, nr = 0, nsl = 0, nsr = 0, minl = 99, maxr = -1;
   double threat = 0.0, prot = 0.0;
@@ -284,26 +283,18 @@ SBD_NI int features(const G& g, double* f) {
     const Ent& e = g.e[g.board[t]];
     const int y = t >> 2;
     if (check_ids && CARD(g, e.card).obs_id == -32768) err = SB_ERR_OBS_ID;
-    const int str = e.strength;
-    const u32 fl = e.fl;
     // the observation uses -1 as "empty": an entity whose strength is exactly -1 would vanish; strengths are >= 0
-    const bool counted = str != -1;
-    const bool mine = (int)(fl & EF_OWNER) == lo;
-    const bool unit = !(fl & EF_STRUCT);
-    const int cs = counted ? str : 0;
-    nl += (mine && unit) ? 1 : 0;
-    nsl += (mine && !unit) ? 1 : 0;
-    nr += (!mine && unit) ? 1 : 0;
-    nsr += (!mine && !unit) ? 1 : 0;
-    minl = (mine && unit && y < minl) ? y : minl;
-    maxr = (!mine && unit && y > maxr) ? y : maxr;
-    sl += mine ? cs : 0;
-    sr += mine ? 0 : cs;
-    // protection: own entities (units and structures) by closeness to the own base; threat: enemy units by closeness to it
-    const double x = __dmul_rn((double)str, fifths(mine ? 5 - y : y + 1));
-    const double acc = __dadd_rn(mine ? prot : threat, x);
-    prot = (mine && counted) ? acc : prot;
-    threat = (!mine && unit && counted) ? acc : threat;
+    const bool counted = e.strength != -1;
+    if (ent_owner(e) == lo) {
+      if (!ent_struct(e)) { nl++; if (y < minl) minl = y; } else nsl++;
+      if (counted) { sl += e.strength; prot = __dadd_rn(prot, __dmul_rn((double)e.strength, fifths(5 - y))); }
+    } else {
+      if (!ent_struct(e)) {
+        nr++; if (y > maxr) maxr = y;
+        if (counted) threat = __dadd_rn(threat, __dmul_rn((double)e.strength, fifths(y + 1)));
+      } else nsr++;
+      if (counted) sr += e.strength;
+    }
   }
   const int tot = sl + sr;
   f[2] = tot == 0 ? 0.0 : ddiv((double)(sl - sr), (double)tot);
