@@ -40,7 +40,10 @@ int sb_sm_count(SbHandle *h);
  * CTA size (128..1024) whose warps change phase together; "refill" = -1 auto, 0/1: finished lanes of the random
  * rollout take the next game from a counter ("refill_ctas" persistent CTAs per SM, "refill_grid" CTAs in total,
  * 0 = auto); "dense" = -1 auto, 0/1: the 32-register builds with 2,048 resident lanes per SM (random rollout, k_step);
- * "heur_wpc" = warps per CTA of the heuristic rollout; "lanes_per_game" is accepted and ignored (retired shape). */
+ * "heur_wpc" = -1 / 4: independent warps (default), 8 / 16 / 32: warps per CTA deciding in step; "heur_refill" = -1 auto
+ * (batches beyond one wave of resident warps), 0/1: a warp of the heuristic rollout whose game ended takes the next game
+ * from a counter; "heur_iw" = -1 auto, 4 / 8 / 16 independent warps per CTA; "heur_grid" = persistent CTAs of that shape
+ * (0 = one wave; tests use tiny grids); "lanes_per_game" is accepted and ignored (retired shape). */
 int sb_set_option(SbHandle *h, const char *key, int value);
 /* kernels launched through this handle so far (bench.py's gpu_launches) */
 uint64_t sb_launch_count(SbHandle *h);
