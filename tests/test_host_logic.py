@@ -231,3 +231,27 @@ def test_config_mirror_matches_reference_defaults():
     with pytest.raises(ValueError):
         EvolutionaryConfig(mu=0)
 
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm: the oracle port on all host threads) runs without a GPU and prints ONE JSON
+    line with the keys the driver reads; ranks other than 0 print nothing."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["unit"] == "env_steps/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert out.returncode == 0 and out.stdout.strip() == ""
