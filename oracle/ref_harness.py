@@ -139,8 +139,35 @@ def ref():
     with open(os.path.join(REF, "actions.txt")) as f:
         ns.actions = f.read().splitlines()
     ns.wn = {float(w): n for n, w in enumerate(weight_table())}
+    # Q14: cards/s203.py:27 `list(set(tiles))` iterates in str-hash order (PYTHONHASHSEED).  The module-level name `set`
+    # is shadowed INSIDE cards.s203 only (the reference source is untouched, same technique as the RNG injection) so the
+    # dedupe keeps first-occurrence order -- the canonical order of the oracle and the CUDA engine.
+    c.s203.set = lambda it: dict.fromkeys(it)
+    ns.activations = _install_activation_counter(c, ns.index)
     _ref = ns
     return ns
+
+
+def _install_activation_counter(cards_mod, index):
+    """Count every activate_ability call per card class (coverage table of tests/golden/make_golden_r2.py).  The wrapper sits
+    OUTSIDE the trigger bookkeeping of card.py:48-62 and only increments a counter."""
+    import collections
+    import functools
+    counts = collections.Counter()
+    for name in index:
+        cls = getattr(cards_mod, name, None)
+        if cls is None or "activate_ability" not in cls.__dict__:
+            continue
+        inner = cls.activate_ability
+
+        def make(inner, name):
+            @functools.wraps(inner)
+            def counted(self, *a, **k):
+                counts[name] += 1
+                return inner(self, *a, **k)
+            return counted
+        cls.activate_ability = make(inner, name)
+    return counts
 
 
 DEFAULT_DECKS = (
@@ -165,6 +192,12 @@ def make_game(seed, decks=None, factions=None):
                 self.random.turn += 1
                 self.random.draw = 0
             return super().step(action)
+
+        def get_observation(self):  # Q12: int(card) raises for UP01-03 (card.py:46) AFTER the step has been applied;
+            try:                     # the bypass lets fixtures pin the effects of those three cards through step()
+                return super().get_observation()
+            except ValueError:
+                return None
 
     env = TurnCountingStormbound.__new__(TurnCountingStormbound)
     env.random = rnd

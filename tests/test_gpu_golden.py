@@ -72,6 +72,36 @@ def test_random_deck_games_rollout_kernel(engine):
     assert unsupported.sum() <= len(unsupported) * 3 // 200
 
 
+def test_card_focus_games_rollout_kernel(engine):
+    """card_focus.npz: all 112 cards (S203 and UP01-03 included) in decks stacked toward each card, reference tapes."""
+    z = load("card_focus.npz")
+    dev = engine.device
+    st = engine.reset(torch.from_numpy(z["seeds"].astype(np.int64)).to(dev), torch.from_numpy(z["decks"]).to(dev),
+                      torch.from_numpy(z["factions"]).to(dev))
+    chain = torch.zeros(len(z["seeds"]), dtype=torch.int64, device=dev)
+    steps = engine.rollout_random(st, 400, chain=chain)
+    host = st.cpu().numpy()
+    steps, chain = steps.cpu().numpy(), chain.cpu().numpy().view(np.uint64)
+    unsupported = (host[:, 18] == 5) | ((host[:, 18] == 6) & ((z["err"] != 2) | (steps <= z["steps"])))
+    clean = (z["err"] == 0) & ~unsupported
+    assert np.array_equal(steps[clean], z["steps"][clean]) and np.array_equal(chain[clean], z["chain"][clean])
+    raised = (z["err"] != 0) & ~unsupported
+    assert (host[raised][:, 18] != 0).all() and np.array_equal(steps[raised], z["steps"][raised] + 1)
+    assert unsupported.sum() <= len(unsupported) * 3 // 200
+
+
+def test_observation_and_features_vs_reference(engine):
+    """sb_observe / sb_features against the reference's own get_observation / StateFeatures (rows a11, a12): exact."""
+    z = load("obs_features.npz")
+    st = torch.from_numpy(z["states"]).to(engine.device)
+    obs, err = engine.observe(st)
+    assert int(err.max()) == 0 and np.array_equal(obs.cpu().numpy(), z["obs"])
+    f, err = engine.features(st)
+    assert int(err.max()) == 0
+    f = f.cpu().numpy()
+    assert np.array_equal(f, z["feat"]), np.abs(f - z["feat"]).max()
+
+
 def test_deck_generation_kernel(engine):
     """sb_generate_decks against the decks the reference's utils.py produced (every schedule phase, both
     random.sample call shapes), batched by identical parameters."""

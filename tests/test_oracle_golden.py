@@ -96,6 +96,56 @@ def test_random_deck_games(oracle):
     assert unsupported <= len(z["seeds"]) * 3 // 200, unsupported  # <= 1.5 %: nested Temple-of-Time memories + ext capacity
 
 
+def test_card_focus_games(oracle):
+    """Every one of the 112 cards in games whose two decks both hold it (tests/golden/make_golden_r2.py): pins the rare
+    branches, S203 (first-occurrence dedupe order, Q14) and UP01-03 (Q12 observation bypass) to the reference."""
+    z = load("card_focus.npz")
+    assert set(z["card"].tolist()) == set(range(1, 113))
+    bad, unsupported = [], 0
+    for i in range(len(z["seeds"])):
+        d, f = z["decks"][i], z["factions"][i]
+        st = oracle.new_game(int(z["seeds"][i]), d[0], d[1], int(f[0]), int(f[1]))
+        _a, dig, _m = oracle.rollout_random(st, 400)
+        kind = int(z["err"][i])
+        if st[18] == 5 or (st[18] == 6 and (kind != 2 or len(dig) <= z["steps"][i])):
+            unsupported += 1
+            continue
+        if kind == 0:
+            ok = len(dig) == z["steps"][i] and chain_of(dig) == int(z["chain"][i]) and final_digest(oracle, st) == int(z["final"][i])
+        else:
+            ok = st[18] != 0 and len(dig) == z["steps"][i] + 1 and chain_of(dig[:-1]) == int(z["chain"][i])
+            if kind == 2:
+                ok = ok and st[18] == 6
+        if not ok:
+            bad.append((int(z["seeds"][i]), int(z["card"][i])))
+    assert not bad, bad[:10]
+    assert unsupported <= len(z["seeds"]) * 3 // 200, unsupported
+
+
+def test_observation_and_features_vs_reference(oracle):
+    """SURVEY rows a11 / a12 pinned: Stormbound.get_observation (games/stormbound.py:400-526, ids card.py:25-46) and
+    StateFeatures.get_feature_vector (evo/features.py:327-342) of the reference on 3,000+ sampled states (default decks,
+    random decks, heuristic games; both flip parities) -- every int32 of the 27x5x4 observation and every feature bit."""
+    z = load("obs_features.npz")
+    assert len(z["states"]) >= 2000 and set(np.unique(z["states"][:, 14]).tolist()) == {0, 1}
+    for i in range(len(z["states"])):
+        st = z["states"][i].copy()
+        obs, err = oracle.observe(st)
+        assert err == 0 and np.array_equal(obs, z["obs"][i]), i
+        f, err = oracle.features(st)
+        assert err == 0 and np.array_equal(f, z["feat"][i]), i
+
+
+def test_card_coverage_table():
+    """every card class with an ability fired at least 20 times in the reference games behind the fixtures"""
+    import json
+    p = os.path.join(G, "card_coverage.json")
+    if not os.path.exists(p):
+        pytest.skip("coverage table not generated")
+    total = json.load(open(p))["total"]
+    assert len(total) >= 83 and min(total.values()) >= 20, {k: v for k, v in total.items() if v < 20}
+
+
 def test_expert_games(oracle):
     """Both seats play Stormbound.expert_action (games/stormbound.py:563-637): every action and every per-step
     state digest of the reference's tapes, default and random decks."""
