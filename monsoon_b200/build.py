@@ -5,9 +5,13 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsb_b200.so")
-SOURCES = ["sb_kernels.cu"]
-DEPS = SOURCES + ["sb_engine.cuh", "sb_effects.cuh", "sb_state_io.cuh", "sb_card_table.inc", "sb_card_ids.h",
-                  os.path.join("..", "..", "include", "sb_b200.h"), os.path.join("..", "..", "include", "sb_state.h")]
+SOURCES = ["sb_kernels.cu", "sbw_kernels.cu"]
+
+
+def _deps():
+    """every file of csrc/ and include/ (a stale library after an edit to any header gives confusing parity failures)"""
+    inc = os.path.join(HERE, "..", "include")
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(inc, f) for f in os.listdir(inc)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
 
@@ -16,7 +20,7 @@ def needs_build():
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build_library(force=False, verbose=False):

@@ -25,6 +25,7 @@
 #include "sb_effects.cuh"
 #include "sb_state_io.cuh"
 #include "sb_es.cuh"
+#include "sbw_launch.h"
 
 #define SB_ABI_VERSION 1
 #define TPB_GAME 64      // threads per CTA for thread-per-game kernels
@@ -618,6 +619,11 @@ struct SbHandle {
   int heur_grid;   // persistent CTAs in refill mode (tests: a grid much smaller than the batch); 0 = one wave
   int heur_refill; // -1 auto, 0 off, 1 on: a warp whose game ended takes the next game from a counter
   int* d_queue;
+  int engine;      // -1 auto, 0 thread-per-game kernels (sb_engine.cuh), 1 warp-per-game kernels (sbw_*.cuh)
+  int w_shape;     // warp engine, random rollout: -1 auto, 0/1/2 = CTA shapes of sbw_rollout_random
+  int w_grid;      // warp engine: persistent CTAs (tests: a grid much smaller than the batch); 0 = fill the chip
+  int w_hshape;    // warp engine, heuristic rollout: -1 auto, 0/1
+  SbwCtx wctx;
   u8* d_pools;    // deck generation: [5][POOL_W] card ids per faction
   int* d_pool_n;
   u8* d_arch;     // staged archetypes [24] + factions [2]
@@ -631,6 +637,24 @@ static int fail(SbHandle* h, cudaError_t e, const char* what) {
 #define LAUNCH_CHECK() do { h->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return fail(h, e_, "kernel launch"); } while (0)
 
 static inline int grid_for(int n, int per_cta) { return (n + per_cta - 1) / per_cta; }
+// Which engine runs a call.  Both give identical results (tests/test_gpu_engines.py); the policy is MEASURED
+// (profiles/r2_summary.md): one game per warp wins while the batch leaves the chip mostly empty -- its chain per env step is
+// 2.5x shorter (6.8 us against 17 us) but every warp is its own instruction stream, so 28+ warps per SM thrash the
+// instruction cache -- and for the record-streaming queries, whose pack / unpack it does one lane per tile; one game per
+// thread wins once ~10 games share a warp's instruction stream.
+enum { WK_ROLLOUT_RANDOM, WK_STEP, WK_LEGAL_MASK, WK_OBSERVE, WK_FEATURES, WK_EXPERT, WK_SELECT, WK_ROLLOUT_HEUR };
+static inline bool use_warp_engine(const SbHandle* h, int kind, int n) {
+  if (h->engine >= 0) return h->engine != 0;
+  switch (kind) {
+    case WK_ROLLOUT_RANDOM: return n <= h->sm_count * 32;   // one wave of 32-warp CTAs (4,096 games: 85 against 73 M env-steps/s)
+    case WK_STEP: return n <= 8192;                          // 4,096 games: 0.077 against 0.143 ms; 65,536: 0.89 against 0.37 ms
+    case WK_LEGAL_MASK: return true;                         // 553 against 409 GB/s at 65,536 records, 822 against 664 at 1 M
+    case WK_OBSERVE: return true;                            // 686 against 380 GB/s at 65,536 records
+    case WK_FEATURES: return n <= 65536;
+    case WK_EXPERT: return n <= 16384;
+    default: return false;                                   // heuristic agent: lane per candidate wins 3.5x
+  }
+}
 static inline int games_per_warp(const SbHandle* h, int n) {
   if (h->gpw > 0 && h->gpw <= 32) return h->gpw;
   // auto (measured, tools/sweep_gpw.py): aim at ~3.5 warps per SM while the batch is small
@@ -740,7 +764,11 @@ int sb_create(int device, SbHandle** out) {
   CK(cudaFuncSetAttribute(k_rollout_heuristic<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(G))));
   CK(cudaFuncSetAttribute(k_rollout_heuristic<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(G))));
   CK(cudaFuncSetAttribute(k_rollout_heuristic<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * sizeof(G))));
-  CK(cudaMalloc(&h->d_queue, 2 * sizeof(int)));  // [0] random rollout lanes, [1] heuristic rollout warps
+  CK(cudaMalloc(&h->d_queue, 4 * sizeof(int)));  // [0] random rollout lanes, [1] heuristic rollout warps, [2..3] warp-engine grids
+  CK(sbw_init());
+  h->wctx.d_cards = h->d_cards; h->wctx.d_wt = h->d_wt; h->wctx.d_queue = h->d_queue + 2; h->wctx.sm_count = h->sm_count;
+  h->engine = -1; h->w_shape = -1; h->w_hshape = -1;
+  { const char* e = getenv("SB_ENGINE"); if (e) h->engine = atoi(e); }
   {  // deck pools: dir(cards) order == card index order; own faction + NEUTRAL (utils.py:74-84)
     static u8 pools[5 * POOL_W];
     int pn[5] = {0, 0, 0, 0, 0};
@@ -853,12 +881,14 @@ int sb_es_inject_diversity(SbHandle* h, uint64_t seed, uint32_t generation, int 
 }
 int sb_legal_mask(SbHandle* h, int n, const uint8_t* states_d, uint32_t* masks_d, void* stream) {
   if (n <= 0) return 0;
+  if (use_warp_engine(h, WK_LEGAL_MASK, n)) { sbw_legal_mask(&h->wctx, n, states_d, masks_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_legal_mask<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, masks_d, h->d_cards, h->d_wt);
   LAUNCH_CHECK();
   return 0;
 }
 int sb_expert_action(SbHandle* h, int n, uint8_t* states_d, uint8_t* actions_d, void* stream) {
   if (n <= 0) return 0;
+  if (use_warp_engine(h, WK_EXPERT, n)) { sbw_expert_action(&h->wctx, n, states_d, actions_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_expert_action<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, actions_d, h->d_cards, h->d_wt);
   LAUNCH_CHECK();
   return 0;
@@ -866,6 +896,11 @@ int sb_expert_action(SbHandle* h, int n, uint8_t* states_d, uint8_t* actions_d, 
 int sb_step(SbHandle* h, int n, uint8_t* states_d, const uint8_t* actions_d, int8_t* reward_d, uint8_t* done_d, uint8_t* err_d,
             uint32_t* next_masks_d, void* stream) {
   if (n <= 0) return 0;
+  if (use_warp_engine(h, WK_STEP, n)) {
+    sbw_step(&h->wctx, n, states_d, actions_d, reward_d, done_d, err_d, next_masks_d, (cudaStream_t)stream);
+    LAUNCH_CHECK();
+    return 0;
+  }
   const int gpw = games_per_warp(h, n);
   int dense = h->dense;
   if (dense < 0) dense = n >= h->sm_count * 1536;
@@ -880,12 +915,14 @@ int sb_step(SbHandle* h, int n, uint8_t* states_d, const uint8_t* actions_d, int
 }
 int sb_observe(SbHandle* h, int n, const uint8_t* states_d, int32_t* obs_d, uint8_t* err_d, void* stream) {
   if (n <= 0) return 0;
+  if (use_warp_engine(h, WK_OBSERVE, n)) { sbw_observe(&h->wctx, n, states_d, obs_d, err_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_observe<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, obs_d, err_d, h->d_cards, h->d_wt);
   LAUNCH_CHECK();
   return 0;
 }
 int sb_features(SbHandle* h, int n, const uint8_t* states_d, double* feat_d, uint8_t* err_d, void* stream) {
   if (n <= 0) return 0;
+  if (use_warp_engine(h, WK_FEATURES, n)) { sbw_features(&h->wctx, n, states_d, feat_d, err_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_features<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, feat_d, err_d, h->d_cards, h->d_wt);
   LAUNCH_CHECK();
   return 0;
@@ -893,6 +930,7 @@ int sb_features(SbHandle* h, int n, const uint8_t* states_d, double* feat_d, uin
 int sb_select_action(SbHandle* h, int n, const uint8_t* states_d, const double* weights_d, uint8_t* actions_d, double* scores_d,
                      void* stream) {
   if (n <= 0) return 0;
+  if (use_warp_engine(h, WK_SELECT, n)) { sbw_select_action(&h->wctx, n, states_d, weights_d, actions_d, scores_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_select_action<<<grid_for(n, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(n, states_d, weights_d, actions_d, scores_d,
                                                                                                 h->d_cards, h->d_wt);
   LAUNCH_CHECK();
@@ -900,6 +938,13 @@ int sb_select_action(SbHandle* h, int n, const uint8_t* states_d, const double* 
 }
 int sb_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max_steps, int32_t* steps_d, uint64_t* chain_d, void* stream) {
   if (n <= 0) return 0;
+  if (use_warp_engine(h, WK_ROLLOUT_RANDOM, n)) {
+    int shape = h->w_shape;
+    if (shape < 0) shape = n <= h->sm_count * 32 ? 5 : 2;  // turn-synchronous 32-warp CTAs while one wave holds the batch (measured)
+    sbw_rollout_random(&h->wctx, n, states_d, max_steps, steps_d, chain_d, shape, h->w_grid, (cudaStream_t)stream);
+    LAUNCH_CHECK();
+    return 0;
+  }
   if (chain_d) launch_rollout_random<true>(h, n, states_d, max_steps, steps_d, chain_d, (cudaStream_t)stream);
   else launch_rollout_random<false>(h, n, states_d, max_steps, steps_d, nullptr, (cudaStream_t)stream);
   LAUNCH_CHECK();
@@ -919,6 +964,10 @@ int sb_set_option(SbHandle* h, const char* key, int value) {
   if (!strcmp(key, "heur_iw")) { h->heur_iw = value; return 0; }
   if (!strcmp(key, "heur_grid")) { h->heur_grid = value; return 0; }
   if (!strcmp(key, "heur_refill")) { h->heur_refill = value; return 0; }
+  if (!strcmp(key, "engine")) { h->engine = value; return 0; }
+  if (!strcmp(key, "w_shape")) { h->w_shape = value; return 0; }
+  if (!strcmp(key, "w_grid")) { h->w_grid = value; return 0; }
+  if (!strcmp(key, "w_hshape")) { h->w_hshape = value; return 0; }
   return -1;
 }
 int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_first_d, const double* w_second_d,
@@ -926,6 +975,12 @@ int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_
                          void* stream) {
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_warp_engine(h, WK_ROLLOUT_HEUR, n)) {
+    sbw_rollout_heuristic(&h->wctx, n, states_d, w_first_d, w_second_d, idx_first_d, idx_second_d, max_steps, result_d, steps_d,
+                          h->w_hshape < 0 ? 0 : h->w_hshape, h->w_grid, st);
+    LAUNCH_CHECK();
+    return 0;
+  }
   int hw = h->heur_wpc;
   if (hw < 0) hw = 4;  // auto (tools/sweep_heur.py): with the shared working-set image independent warps win at every batch size;
                        // limiting resident threads to fit L2 only loses (tools/sweep_heur_resident.py, removed knob)

@@ -518,6 +518,14 @@ SBW_NI void w_set_path(WG* wg, int id, int on_play, int extra_movement) {  // un
   *reinterpret_cast<u64*>(wg->e_path[id]) = dest;
   wg->e_plen[id] = (u8)nd;
 }
+// the common case of unit.py:78-122 inline: one step straight ahead (turn start / command, unit not confused)
+SBW_FI void w_set_path_step(WG* wg, int id) {
+  if (w_st(wg, id, SB_ST_CONFUSED)) { w_set_path(wg, id, 0, 0); return; }
+  const int t = wg->e_pos[id];
+  const bool is_local = w_owner(wg, id) == wg->local_order;
+  wg->e_path[id][0] = (u8)(t + 4 + (is_local ? -4 : 4));  // enc = (y + 1) * 4 + x of the tile one row ahead
+  wg->e_plen[id] = 1;
+}
 SBW_NI void w_unit_move(WG* wg, int id) {  // unit.py:124-203
   W_SHARED(wg);
   if (wg->depth > MAXDEPTH) { WERR(wg, SB_ERR_DEPTH); return; }
@@ -595,7 +603,7 @@ SBW_NI void wv_command(WG* wg, int id) {  // unit.py:282-289
   W_SHARED(wg);
   const u8 cache = wg->e_fl[id] & WEF_FIXED;
   wg->e_fl[id] |= WEF_FIXED;
-  w_set_path(wg, id, 0, 0);
+  w_set_path_step(wg, id);
   w_unit_move(wg, id);
   wg->e_fl[id] = (u8)((wg->e_fl[id] & ~WEF_FIXED) | cache);
 }
@@ -834,7 +842,7 @@ SBW_NI void w_to_next_turn(WG* wg) {  // board.py:117-145
   }
   n = w_snapshot_ids(wg, w_targets(wg, cur, w_mkT(TK_UNIT, TS_FRIENDLY), PT_NONE));
 #pragma unroll 1
-  for (int i = 0; i < n; i++) { const int id = wg->tn_ids[i]; w_set_path(wg, id, 0, 0); w_unit_move(wg, id); }  // snapshot incl. ghosts (Q21)
+  for (int i = 0; i < n; i++) { const int id = wg->tn_ids[i]; w_set_path_step(wg, id); w_unit_move(wg, id); }  // snapshot incl. ghosts (Q21)
   wg->phase = PH_PLAY;
 }
 

@@ -204,6 +204,121 @@ class Game:
         return self._action_names[action_number]
 
 
+class EvolutionaryStormbound:
+    """games/evolutionary_stormbound.py:21-232: the same engine with the decks of a DeckEvolutionConfig schedule.
+
+    Mirrors the reference class member for member, including what it does NOT have: there is no `.env` attribute,
+    so callers that reach for `game.env` (evo/game_adapter.py:334-371, evo/fitness.py:216) get the AttributeError the reference
+    gives them -- FitnessEvaluator's faithful mode turns that into a draw exactly like evo/fitness.py:223-225.  `reset()`
+    re-deals (:129-152), unlike Stormbound.reset; `step` returns the raw 0/1 reward (Stormbound.step, no x10 of Game.step).
+    The reference keeps dealing from one RandomState; here deal number k of a game uses the stream key seed + k * 2^32.
+    """
+
+    def __init__(self, seed=None, generation=0, deck_config=None, device=0, engine=None):
+        from .evo import DeckEvolutionConfig
+        self.eng = engine or get_engine(device)
+        if seed is None:
+            seed = int(np.random.SeedSequence().entropy & 0x7FFFFFFF)
+        self.seed = int(seed)
+        self.generation = generation
+        if deck_config is None:
+            deck_config = self._create_default_deck_config()
+        self.deck_config = deck_config
+        self.actions = _ACTION_NAMES
+        self.player = 1
+        self._deals = 0
+        self._host_rng = np.random.RandomState(self.seed & 0xFFFFFFFF)  # expert_agent placeholder only (:221-227)
+        self._deal()
+
+    @staticmethod
+    def _create_default_deck_config():  # :77-122
+        from .evo import DeckEvolutionConfig
+        return DeckEvolutionConfig(DEFAULT_DECKS[0], DEFAULT_DECKS[1], exploit_generations=30, explore_generations=30,
+                                   max_random_ratio=0.5, balance_archetype_ratio=0.7)
+
+    def _deal(self):
+        dev = self.eng.device
+        key = (self.seed + (self._deals << 32)) & 0x7FFFFFFFFFFFFFFF
+        self._deals += 1
+        seeds = torch.tensor([key], dtype=torch.int64, device=dev)
+        decks, factions = self.deck_config.generate_batch(self.eng, seeds, self.generation)
+        names = self.deck_config._names
+        d = decks[0].cpu().numpy()
+        self.player1_deck, self.player2_deck = [names[c] for c in d[0]], [names[c] for c in d[1]]
+        self.state = self.eng.reset(seeds, decks, factions)
+        self.player = 1
+        self._host_cache = None
+
+    def _host(self):
+        if self._host_cache is None:
+            self._host_cache = self.state[0].cpu().numpy()
+        return self._host_cache
+
+    def to_play(self):
+        return 0 if self.player == 1 else 1
+
+    def reset(self):
+        self._deal()
+        return self.get_observation()
+
+    def set_generation(self, generation):
+        self.generation = generation  # applied by the next reset(), like the reference
+
+    def get_phase_info(self):
+        return self.deck_config.get_phase_info(self.generation)
+
+    def step(self, action):
+        a = torch.tensor([int(action)], dtype=torch.uint8, device=self.eng.device)
+        reward, done, err = self.eng.step(self.state, a)
+        self._host_cache = None
+        if int(err[0]):
+            raise EngineError(int(err[0]))
+        self.player = int(np.int8(self._host()[16]))
+        return self.get_observation(), int(reward[0]), bool(done[0])
+
+    def legal_actions(self):
+        return mask_to_actions(self.eng.legal_mask(self.state)[0].cpu().numpy().view(np.uint32))
+
+    def get_observation(self):
+        obs, err = self.eng.observe(self.state)
+        if int(err[0]):
+            raise EngineError(int(err[0]))
+        return obs[0].cpu().numpy()
+
+    def have_winner(self):
+        st = self._host()
+        bases = [int(np.frombuffer(st[32 + 104 * o:34 + 104 * o].tobytes(), dtype="<i2")[0]) for o in (0, 1)]
+        return bases[0] < 0 or bases[1] < 0
+
+    def clone(self):
+        g = EvolutionaryStormbound.__new__(EvolutionaryStormbound)
+        g.__dict__.update(self.__dict__)
+        g.state = self.state.clone()
+        g._host_cache = None
+        return g
+
+    def render(self):
+        info = self.get_phase_info()
+        print("=== Evolutionary Stormbound (Generation %d) ===" % self.generation)
+        print("Phase: %s | Random Ratio: %.2f" % (info["phase"], info["random_ratio"]))
+        print(self.get_observation()[[0, 1, 16, 17]])
+
+    def close(self):
+        pass
+
+    def expert_agent(self):  # :221-227 "placeholder": a uniformly random legal action, else PASS
+        legal = self.legal_actions()
+        return int(self._host_rng.choice(legal)) if legal else 155
+
+    def action_to_string(self, action_number):
+        if action_number < len(self.actions):
+            return self.actions[action_number]
+        return None
+
+    def human_to_action(self):
+        return int(input("action (0-155): "))
+
+
 def _make_action_names():
     """actions.txt equivalent, generated from the comment block enums.py:10-36 / :85-105."""
     names = []
@@ -226,4 +341,4 @@ def _make_action_names():
 
 
 _ACTION_NAMES = _make_action_names()
-__all__ = ["Game", "BatchedGames", "EngineError", "mask_to_actions", "DEFAULT_DECKS", "DEFAULT_FACTIONS", "STATE_BYTES"]
+__all__ = ["Game", "EvolutionaryStormbound", "BatchedGames", "EngineError", "mask_to_actions", "DEFAULT_DECKS", "DEFAULT_FACTIONS", "STATE_BYTES"]

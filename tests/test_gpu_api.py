@@ -198,3 +198,32 @@ def test_dense_variants_give_identical_states(engine):
     finally:
         engine.set_option("dense", -1)
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_evolutionary_stormbound(engine):
+    """EvolutionaryStormbound mirror (games/evolutionary_stormbound.py:21-232): exploit-phase decks are the archetypes, the
+    game steps like Game on the same stream key, reset() re-deals, there is no `.env` (Q17)."""
+    from monsoon_b200.games import EvolutionaryStormbound, Game
+    from monsoon_b200.engine import DEFAULT_DECKS, DEFAULT_FACTIONS
+    g = EvolutionaryStormbound(seed=11, generation=0, engine=engine)
+    assert not hasattr(g, "env")
+    assert g.player1_deck == list(DEFAULT_DECKS[0]) and g.player2_deck == list(DEFAULT_DECKS[1])
+    # utils.py:152-153: the faction is the one of the archetype's first card (UA07 is NEUTRAL), not DEFAULT_FACTIONS
+    ref = Game(seed=11, decks=DEFAULT_DECKS, factions=(g.deck_config.player1_faction, g.deck_config.player2_faction), engine=engine)
+    rs = np.random.RandomState(0)
+    for _ in range(40):
+        la = g.legal_actions()
+        assert la == ref.legal_actions() and g.to_play() == ref.to_play()
+        a = int(la[rs.randint(len(la))])
+        obs, reward, done = g.step(a)
+        obs2, reward2, done2 = ref.step(a)
+        assert np.array_equal(obs, obs2) and reward * 10 == reward2 and done == done2  # Game.step multiplies by 10 (:140)
+        if g.have_winner():
+            break
+    first = g.state.clone()
+    g.reset()
+    assert not torch.equal(first, g.state) and g.to_play() == 0
+    g.set_generation(45)  # explore phase of the default schedule: part of each deck is random
+    g.reset()
+    assert g.get_phase_info()["phase"] == "Explore" and len(g.player1_deck) == 12
+    assert isinstance(g.expert_agent(), int) and g.action_to_string(155) == "Pass the turn"

@@ -255,3 +255,27 @@ def test_bench_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, env=env, cwd=root)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_evolutionary_stormbound_mirror_surface():
+    """games/evolutionary_stormbound.py:21-232: same public members, and -- like the reference -- no `.env`,
+    which is what makes the reference's adapter / evaluator fall into their AttributeError branches with this class."""
+    from monsoon_b200.games import EvolutionaryStormbound as Mirror
+    want = {"to_play", "reset", "set_generation", "get_phase_info", "step", "legal_actions", "get_observation", "have_winner",
+            "render", "close", "expert_agent", "action_to_string"}
+    ref_dir = "/root/reference"
+    if os.path.isdir(ref_dir):  # build container: read the member list off the reference class itself
+        import ref_harness as h
+        h.ref()
+        cwd = os.getcwd()
+        os.chdir(ref_dir)
+        try:
+            from games.evolutionary_stormbound import EvolutionaryStormbound as Ref
+        finally:
+            os.chdir(cwd)
+        ref_public = {n for n in vars(Ref) if not n.startswith("_") and callable(getattr(Ref, n))}
+        assert ref_public == want, ref_public ^ want
+        assert not hasattr(Ref, "env")
+    have = {n for n in vars(Mirror) if not n.startswith("_") and callable(getattr(Mirror, n))}
+    assert want <= have, want - have
+    assert "env" not in vars(Mirror) and "env" not in Mirror.__init__.__code__.co_names

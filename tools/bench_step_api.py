@@ -6,7 +6,8 @@ sys.path[:0] = [ROOT]
 import torch
 from monsoon_b200.engine import Engine
 eng = Engine(0); dev = eng.device
-for n in (4096, 65536, 262144, 1048576):
+for engine_id, n in [(e, n) for n in (256, 4096, 65536, 262144, 1048576) for e in (0, 1)]:
+    eng.set_option("engine", engine_id)
     seeds = torch.arange(n, dtype=torch.int64, device=dev)
     st = eng.reset(seeds)
     eng.rollout_random(st, max_steps=20)            # mid-game states
@@ -32,4 +33,4 @@ for n in (4096, 65536, 262144, 1048576):
         if it >= 2: times.append(e0.elapsed_time(e1))
         acts = pick(nmask)
     ms = sum(times) / len(times)
-    print("k_step n=%8d  %8.3f ms/launch  %8.1f M env-steps/s  HBM-equivalent %7.1f GB/s (%.2f %% of 6550)" % (n, ms, n / ms / 1e3, 1047 * n / ms / 1e6, 1047 * n / ms / 1e6 / 65.5), flush=True)
+    print(("thread" if engine_id == 0 else "warp  ") + " k_step n=%8d  %8.3f ms/launch  %8.1f M env-steps/s  HBM-equivalent %7.1f GB/s (%.2f %% of 6550)" % (n, ms, n / ms / 1e3, 1047 * n / ms / 1e6, 1047 * n / ms / 1e6 / 65.5), flush=True)
