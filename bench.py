@@ -24,11 +24,37 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT]
 
 B_STEP = 2 * 512 + 1 + 20 + 2  # algorithmic bytes per env step: state in+out, action, mask, reward/done
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_rollout_random launch at the named workload, from the
-# ncu --set full capture profiles/r1_rollout_4096_final_metrics.txt (19.01 MB read + 5.63 MB written)
-NCU_TRAFFIC_BYTES_PER_LAUNCH_4096 = 24_646_656
 METRIC = "env_steps_per_sec"
 WORKLOAD = "4096 parallel games/GPU, uniform-random legal agents, default decks, played to completion (max 400 steps)"
+# What ncu measured for ONE launch of the kernels behind the three legs (profiles/r2_summary.md; `--set full`, one capture
+# each).  Static facts of the kernels (instructions per env step, lanes per instruction, DRAM bytes per launch): the live
+# part of `roofline` is the CUDA-event duration measured in this run.
+NCU = {
+    # named workload, 4,096 games: kw_rollout_random<32,1,true> (one game per warp, turn-synchronous 32-warp CTAs)
+    "rollout_4096": {"kernel": "kw_rollout_random<32,1,true>", "capture": "profiles/r2_w4096_s5_metrics.txt", "dram_bytes": None,
+                     "warp_inst_per_env_step": None, "threads_per_inst": None, "issue_active_pct": None},
+    # saturated leg, 262,144 games: k_rollout_random<false,1024,true,2> (one game per thread, lane refill, 32-register build)
+    "rollout_262144": {"kernel": "k_rollout_random<false,1024,true,2>", "capture": "profiles/r1_rollout_262144_final_metrics.txt",
+                       "dram_bytes": 82.7e9, "warp_inst_per_env_step": 8.95e9 / 18.8e6, "threads_per_inst": 4.41, "issue_active_pct": 17.9},
+    # evo leg, 65,536 heuristic games: k_rollout_heuristic<8,false> (warp per game, lane per candidate, warp refill)
+    "heuristic_65536": {"kernel": "k_rollout_heuristic<8,false>", "capture": "profiles/r1_heur_65536_s2_refill_metrics.txt",
+                        "dram_bytes": 1060e9, "warp_inst_per_env_step": None, "threads_per_inst": 11.2, "issue_active_pct": 15.8},
+}
+
+
+def load_ncu_constants():
+    """profiles/r2_ncu_constants.json (written by tools/ncu_constants.py from the committed captures) overrides the table above"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_constants.json")) as f:
+            for k, v in json.load(f).items():
+                NCU.setdefault(k, {}).update(v)
+    except Exception:  # noqa: BLE001
+        pass
+
+
+def bench_config(n_games_per_gpu=4096):
+    """the SAME dict in both arms (the driver compares them); everything else about a run is a top-level key"""
+    return {"workload": WORKLOAD, "games_per_gpu": n_games_per_gpu}
 
 
 def measured_peak():
@@ -108,6 +134,18 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(sm), "how": self.how}
 
 
+def issue_roofline(key, env_steps_per_launch, seconds_per_launch, sm_count, sm_mhz):
+    """issue-slot roofline of a rollout kernel: warp instructions per second against sm_count x 4 schedulers x clock"""
+    c = NCU.get(key, {})
+    peak = sm_count * 4 * sm_mhz * 1e6
+    out = {"peak_warp_inst_per_s": peak, "threads_per_inst": c.get("threads_per_inst"), "issue_active_pct": c.get("issue_active_pct"),
+           "warp_inst_per_env_step": c.get("warp_inst_per_env_step"), "source": c.get("capture")}
+    if c.get("warp_inst_per_env_step"):
+        out["achieved_warp_inst_per_s"] = c["warp_inst_per_env_step"] * env_steps_per_launch / seconds_per_launch
+        out["frac"] = out["achieved_warp_inst_per_s"] / peak
+    return out
+
+
 def cpu_port(n_games, threads, seed0=10_000_000):
     """The oracle port (plain C restatement of the reference engine) on `threads` host threads."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -124,6 +162,18 @@ def cpu_port(n_games, threads, seed0=10_000_000):
     return total, dt
 
 
+def python_reference_leg(n_games=256):
+    """the reference's own Python engine, unmodified, multiprocessing.Pool(os.cpu_count()) on the
+    box's host cores, a bounded sample (256 whole games) of the same workload.  None when no copy of the reference is at hand."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_python_baseline
+        r = ref_python_baseline.run(n_games)
+        return None if r is None else {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    except Exception as e:  # noqa: BLE001 -- a reported baseline must never take the bench line down
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_reference(args):
     """--impl reference: the reference is pure Python and cannot travel to the GPU box; its CPU arm is the
     oracle port (kind "port"), all host threads, on a bounded sample of the same workload per step."""
@@ -131,7 +181,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_games = 4096
+    n_games = 4096 * max(args.gpus, 1)  # the job's games per step: 4,096 per GPU, like the GPU arm at this N
     for _ in range(args.warmup):
         cpu_port(n_games, threads)
     tot_steps, tot_t = 0, 0.0
@@ -141,15 +191,21 @@ def run_reference(args):
         tot_t += dt
     value = tot_steps / tot_t
     sample = "%d games (default decks, random agents, to completion) per step; dealing excluded from the clock" % n_games
-    print(json.dumps({
+    line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "env_steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm = oracle port (C restatement of the Python reference), not the Python itself"},
+        "config": bench_config(),
+        "notes": "CPU arm = the oracle port (plain-C restatement of the Python reference, ~1,000x faster per core than the Python), "
+                 "all host threads; the reference's own Python engine is timed beside it in cpu_baseline_reference",
         "cpu_baseline": {"value": value, "unit": "env_steps/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env_steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "games_per_sec": n_games * args.steps / tot_t,
-    }))
+    }
+    py = python_reference_leg()
+    if py:
+        line["cpu_baseline_reference"] = py
+    print(json.dumps(line))
 
 
 def main():
@@ -165,6 +221,7 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    load_ncu_constants()
 
     import numpy as np
     import torch
@@ -282,7 +339,10 @@ def main():
             dist.all_reduce(sv, op=dist.ReduceOp.SUM)
             best, ssteps = float(mx[0]), float(sv[1])
         sat = {"games_per_gpu": ns, "value": ssteps / (best * 1e-3), "unit": "env_steps/s", "ms": best,
-               "games_per_sec": ns * world / (best * 1e-3), "hbm_equiv_gbs": B_STEP * ssteps / (best * 1e-3) / 1e9}
+               "games_per_sec": ns * world / (best * 1e-3), "hbm_equiv_gbs": B_STEP * ssteps / (best * 1e-3) / 1e9,
+               "roofline": {"kernel": NCU["rollout_262144"]["kernel"], "traffic": NCU["rollout_262144"]["dram_bytes"],
+                            "traffic_unit": "bytes per launch (ncu, %s)" % NCU["rollout_262144"]["capture"],
+                            "issue": issue_roofline("rollout_262144", ssteps / world, best * 1e-3, eng.sm_count, 1965)}}
         del sstates
 
     # the third part of BASELINE.json's metric: wall time of one evo fitness evaluation (config 3: population
@@ -315,7 +375,12 @@ def main():
                 dist.barrier()
             walls.append(time.perf_counter() - t0)
         evo = {"config": "pop 256 x 256 games vs heuristic baseline (65,536 games, max 400 steps)", "generation_wall_s": walls[-1],
-               "games_per_sec": 65536 / walls[-1], "mean_fitness": float(np.mean(fit))}
+               "games_per_sec": 65536 / walls[-1], "mean_fitness": float(np.mean(fit)),
+               "aborted_games": {"like_reference": ev.last_aborted[0], "engine_limit": ev.last_aborted[1]},
+               "roofline": {"kernel": NCU["heuristic_65536"]["kernel"], "traffic": NCU["heuristic_65536"]["dram_bytes"],
+                            "traffic_unit": "bytes per 65,536-game launch on one GPU (ncu, %s)" % NCU["heuristic_65536"]["capture"],
+                            "threads_per_inst": NCU["heuristic_65536"]["threads_per_inst"],
+                            "issue_active_pct": NCU["heuristic_65536"]["issue_active_pct"]}}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -325,17 +390,25 @@ def main():
             "metric": METRIC, "value": value, "unit": "env_steps/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "games_per_gpu": n, "l2": "flushed between timed iterations (256 MiB fill)",
-                       "timing": "CUDA events on the launch stream, reset+rollout kernels, max over ranks"},
+            "config": bench_config(n),
+            "notes": {"l2": "flushed between timed iterations (256 MiB fill)",
+                      "timing": "CUDA events on the launch stream, reset+rollout kernels, max over ranks",
+                      "e2e": "sb_rollout_random_host: pinned host seeds in, final states + step counts out, H2D + both kernels + D2H + "
+                             "stream sync inside a host wall clock; other seeds than the event-timed passes, no L2 flush between calls",
+                      "engine": "default policy: one game per warp (kw_rollout_random, turn-synchronous 32-warp CTAs) while the batch fits "
+                                "one wave, one game per thread (k_rollout_random) beyond; both bit-identical (tests/test_gpu_engines.py)"},
             "games_per_sec": n * world * args.steps / (t_ms * 1e-3),
             "env_steps_per_game": total_steps / (n * world * args.steps),
             "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": "env_steps/s", "h2d_bytes_per_step": n * 8 + 24 + 2,
                     "d2h_bytes_per_step": n * 512 + n * 4},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH_4096 if n == 4096 else None,
-                         "traffic_unit": "bytes per launch (ncu, profiles/r1_summary.md)", "kernel": "k_rollout_random", "peak_source": peak_src,
-                         "algorithmic_bytes_per_env_step": B_STEP},
+                         "traffic": NCU["rollout_4096"]["dram_bytes"] if n == 4096 else None,
+                         "traffic_unit": "bytes per launch (ncu --set full, %s)" % NCU["rollout_4096"]["capture"],
+                         "kernel": NCU["rollout_4096"]["kernel"], "peak_source": peak_src, "algorithmic_bytes_per_env_step": B_STEP,
+                         # what actually bounds a whole-game rollout: warp-instruction issue, not HBM
+                         "issue": issue_roofline("rollout_4096", steps_per_launch, t_roll_ms / args.steps * 1e-3, eng.sm_count,
+                                                 (sampler.summary().get("sm_max_mhz") or 1965))},
             "clocks": sampler.summary(),
         }
         if sat:
@@ -348,6 +421,9 @@ def main():
             s, dt = cpu_port(ng, threads)
             out["cpu_baseline"] = {"value": s / dt, "unit": "env_steps/s", "cores": threads, "kind": "port",
                                    "sample": "%d games of the same workload (%d env steps), rollouts only, in %.2f s wall on %d threads" % (ng, s, dt, threads)}
+            py = python_reference_leg()
+            if py:
+                out["cpu_baseline_reference"] = py
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

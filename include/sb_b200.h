@@ -133,6 +133,12 @@ int sb_rollout_heuristic(SbHandle *h, int n, uint8_t *states_d, const double *w_
 int sb_accumulate_fitness(SbHandle *h, int n, const int8_t *result_d, const int32_t *idx_first_d, int32_t *counts_d,
                           void *stream);
 
+/* Games a rollout aborted (result -2), split by cause: out_d i32[2] += {games stopped by an exception the reference raises
+ * too (state.err 1..4; evo/fitness.py:208-210 scores them as a draw as well), games stopped by a limit of this engine
+ * (state.err 5..7: SB_ERR_UNSUPPORTED / OVERFLOW / DEPTH -- the reference would have kept playing)}.  The evaluator
+ * reports both and warns when the second exceeds 1 % of the games. */
+int sb_count_aborted(SbHandle *h, int n, const uint8_t *states_d, const int8_t *result_d, int32_t *out_d, void *stream);
+
 /* Host-buffer variants (pinned or pageable host memory; H2D + kernel + D2H + sync inside): the e2e path. */
 int sb_step_host(SbHandle *h, int n, uint8_t *states, const uint8_t *actions, int8_t *reward, uint8_t *done,
                  uint8_t *err, uint32_t *next_masks);

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sb_rollout_random": (_int, [_vp, _int, _vp, _int, _vp, _vp, _vp]),
     "sb_rollout_heuristic": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "sb_accumulate_fitness": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
+    "sb_count_aborted": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "sb_step_host": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_rollout_random_host": (_int, [_vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp, _vp]),
 }

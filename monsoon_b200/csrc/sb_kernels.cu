@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(TPB_GAME) k_reset(int n, const unsigned long l
     p.replacable = 1; p.leftmost = 1; p.faction = fc[o]; p.n_hand = 0;
     i8 order[SB_DECK_MAX];
     int nd = n_deck < SB_DECK_MAX ? n_deck : SB_DECK_MAX;
-    for (int k = 0; k < nd; k++) order[k] = (i8)dk[o * n_deck + k];
+    for (int k = 0; k < nd; k++) {  // a card id outside the table would index shared memory out of bounds: flag the game instead
+      const int cid = dk[o * n_deck + k];
+      if (cid <= 0 || cid >= SBC_COUNT) { GERR(g, SB_ERR_INDEX); order[k] = (i8)SBC_TOKEN_UNIT0; } else order[k] = (i8)cid;
+    }
     shuffle(g, order, nd);  // player.py:28
     p.n_deck = (u8)nd;
     for (int k = 0; k < nd; k++) {  // player.py:30-32
@@ -593,6 +596,16 @@ __global__ void k_accumulate_fitness(int n, const i8* result, const int* idx_fir
   atomicAdd(&counts[ind * 3 + (r == 0 ? 0 : r == 1 ? 2 : 1)], 1);
 }
 
+// games a rollout aborted (result -2), split by who would have raised: out[0] += codes the reference raises too
+// (SB_ERR_NONE_TARGET .. SB_ERR_OBS_ID: its callers turn them into a draw as well), out[1] += limits of THIS engine
+// (SB_ERR_UNSUPPORTED / OVERFLOW / DEPTH: the reference would have kept playing)
+__global__ void k_count_aborted(int n, const u8* states, const i8* result, int* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || result[i] != -2) return;
+  const int code = states[(size_t)i * SB_STATE_BYTES + 18];
+  atomicAdd(&out[code >= SB_ERR_UNSUPPORTED ? 1 : 0], 1);
+}
+
 // ================================================================ host side / C ABI
 #include "sb_card_table_host.h"
 
@@ -628,6 +641,19 @@ struct SbHandle {
   int* d_pool_n;
   u8* d_arch;     // staged archetypes [24] + factions [2]
 };
+
+// Every entry point runs with the handle's device current and restores the caller's device afterwards: two handles in
+// one process (or a caller whose current device is another GPU) launch on the right device without the library ever
+// changing the caller's device for good.
+struct DevGuard {
+  int prev;
+  bool switched;
+  explicit DevGuard(int device) : prev(-1), switched(false) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define DEV_GUARD(h) DevGuard dev_guard_((h)->device)
 
 static int fail(SbHandle* h, cudaError_t e, const char* what) {
   if (h) snprintf(h->err, sizeof h->err, "%s: %s", what, cudaGetErrorString(e));
@@ -724,7 +750,7 @@ int sb_create(int device, SbHandle** out) {
   if (e != cudaSuccess || count == 0 || device >= count) { free(h); return e != cudaSuccess ? -(int)e : -(int)cudaErrorNoDevice; }
   h->device = device;
   *out = h;
-  CK(cudaSetDevice(device));
+  DEV_GUARD(h);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->sm_count = prop.multiProcessorCount;
@@ -793,7 +819,7 @@ int sb_create(int device, SbHandle** out) {
 }
 int sb_destroy(SbHandle* h) {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  DEV_GUARD(h);
   if (h->d_cards) cudaFree(h->d_cards);
   if (h->d_wt) cudaFree(h->d_wt);
   if (h->d_queue) cudaFree(h->d_queue);
@@ -813,6 +839,7 @@ uint64_t sb_launch_count(SbHandle* h) { return h->launches; }
 
 int sb_reset(SbHandle* h, int n, const uint64_t* seeds_d, const uint8_t* decks_d, int n_deck, int decks_shared,
              const uint8_t* factions_d, uint8_t* states_d, void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   k_reset<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, (const unsigned long long*)seeds_d, decks_d, n_deck,
                                                                         decks_shared, factions_d, states_d, h->d_cards, h->d_wt);
@@ -822,6 +849,7 @@ int sb_reset(SbHandle* h, int n, const uint64_t* seeds_d, const uint8_t* decks_d
 int sb_generate_decks(SbHandle* h, int n, const uint64_t* seeds_d, uint32_t generation, int mode, int n_preserve, double q,
                       const uint8_t* archetypes, const uint8_t* arch_factions, const uint8_t* factions_d, uint8_t* decks_d,
                       uint8_t* factions_out_d, void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   if (mode < 0 || mode > 3 || (mode != 3 && (!archetypes || !arch_factions)) || (mode == 3 && !factions_d)) {
     snprintf(h->err, sizeof h->err, "sb_generate_decks: bad mode/arguments");
@@ -850,6 +878,7 @@ static int es_args_ok(SbHandle* h, int mu, int nf, const char* what) {
 }
 int sb_es_offspring(SbHandle* h, uint64_t seed, uint32_t generation, int mu, int lambda, int n_features, double tau, double tau_prime,
                     double min_sigma, double* w_d, double* s_d, int32_t* parents_d, void* stream) {
+  DEV_GUARD(h);
   if (!es_args_ok(h, mu, n_features, "sb_es_offspring")) return -1;
   if (lambda <= 0) return 0;
   k_es_offspring<<<grid_for(lambda, 128), 128, 0, (cudaStream_t)stream>>>(seed, generation, mu, lambda, n_features, tau, tau_prime, min_sigma,
@@ -859,6 +888,7 @@ int sb_es_offspring(SbHandle* h, uint64_t seed, uint32_t generation, int mu, int
 }
 int sb_es_select(SbHandle* h, int total, int mu, int n_features, const double* fitness_d, const double* w_d, const double* s_d,
                  double* w_out_d, double* s_out_d, double* fit_out_d, int32_t* order_d, void* stream) {
+  DEV_GUARD(h);
   if (!es_args_ok(h, mu, n_features, "sb_es_select")) return -1;
   if (total < mu) { snprintf(h->err, sizeof h->err, "sb_es_select: total < mu"); return -1; }
   k_es_select<<<grid_for(total, 128), 128, 0, (cudaStream_t)stream>>>(total, mu, n_features, fitness_d, w_d, s_d, w_out_d, s_out_d, fit_out_d, order_d);
@@ -866,6 +896,7 @@ int sb_es_select(SbHandle* h, int total, int mu, int n_features, const double* f
   return 0;
 }
 int sb_es_reset_sigmas(SbHandle* h, uint64_t seed, uint32_t generation, int mu, int n_features, double initial_sigma, double* s_d, void* stream) {
+  DEV_GUARD(h);
   if (!es_args_ok(h, mu, n_features, "sb_es_reset_sigmas")) return -1;
   k_es_reset_sigmas<<<grid_for(mu, 128), 128, 0, (cudaStream_t)stream>>>(seed, generation, mu, n_features, initial_sigma, s_d);
   LAUNCH_CHECK();
@@ -873,6 +904,7 @@ int sb_es_reset_sigmas(SbHandle* h, uint64_t seed, uint32_t generation, int mu, 
 }
 int sb_es_inject_diversity(SbHandle* h, uint64_t seed, uint32_t generation, int mu, int n_features, double tau, double tau_prime,
                            double min_sigma, double initial_sigma, double* w_d, double* s_d, int32_t* chosen_d, void* stream) {
+  DEV_GUARD(h);
   if (!es_args_ok(h, mu, n_features, "sb_es_inject_diversity")) return -1;
   k_es_inject_diversity<<<1, 256, 0, (cudaStream_t)stream>>>(seed, generation, mu, n_features, tau, tau_prime, min_sigma, initial_sigma, w_d, s_d,
                                                              chosen_d);
@@ -880,6 +912,7 @@ int sb_es_inject_diversity(SbHandle* h, uint64_t seed, uint32_t generation, int 
   return 0;
 }
 int sb_legal_mask(SbHandle* h, int n, const uint8_t* states_d, uint32_t* masks_d, void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   if (use_warp_engine(h, WK_LEGAL_MASK, n)) { sbw_legal_mask(&h->wctx, n, states_d, masks_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_legal_mask<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, masks_d, h->d_cards, h->d_wt);
@@ -887,6 +920,7 @@ int sb_legal_mask(SbHandle* h, int n, const uint8_t* states_d, uint32_t* masks_d
   return 0;
 }
 int sb_expert_action(SbHandle* h, int n, uint8_t* states_d, uint8_t* actions_d, void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   if (use_warp_engine(h, WK_EXPERT, n)) { sbw_expert_action(&h->wctx, n, states_d, actions_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_expert_action<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, actions_d, h->d_cards, h->d_wt);
@@ -895,6 +929,7 @@ int sb_expert_action(SbHandle* h, int n, uint8_t* states_d, uint8_t* actions_d, 
 }
 int sb_step(SbHandle* h, int n, uint8_t* states_d, const uint8_t* actions_d, int8_t* reward_d, uint8_t* done_d, uint8_t* err_d,
             uint32_t* next_masks_d, void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   if (use_warp_engine(h, WK_STEP, n)) {
     sbw_step(&h->wctx, n, states_d, actions_d, reward_d, done_d, err_d, next_masks_d, (cudaStream_t)stream);
@@ -914,6 +949,7 @@ int sb_step(SbHandle* h, int n, uint8_t* states_d, const uint8_t* actions_d, int
   return 0;
 }
 int sb_observe(SbHandle* h, int n, const uint8_t* states_d, int32_t* obs_d, uint8_t* err_d, void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   if (use_warp_engine(h, WK_OBSERVE, n)) { sbw_observe(&h->wctx, n, states_d, obs_d, err_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_observe<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, obs_d, err_d, h->d_cards, h->d_wt);
@@ -921,6 +957,7 @@ int sb_observe(SbHandle* h, int n, const uint8_t* states_d, int32_t* obs_d, uint
   return 0;
 }
 int sb_features(SbHandle* h, int n, const uint8_t* states_d, double* feat_d, uint8_t* err_d, void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   if (use_warp_engine(h, WK_FEATURES, n)) { sbw_features(&h->wctx, n, states_d, feat_d, err_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_features<<<grid_for(n, TPB_GAME), TPB_GAME, 0, (cudaStream_t)stream>>>(n, states_d, feat_d, err_d, h->d_cards, h->d_wt);
@@ -929,6 +966,7 @@ int sb_features(SbHandle* h, int n, const uint8_t* states_d, double* feat_d, uin
 }
 int sb_select_action(SbHandle* h, int n, const uint8_t* states_d, const double* weights_d, uint8_t* actions_d, double* scores_d,
                      void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   if (use_warp_engine(h, WK_SELECT, n)) { sbw_select_action(&h->wctx, n, states_d, weights_d, actions_d, scores_d, (cudaStream_t)stream); LAUNCH_CHECK(); return 0; }
   k_select_action<<<grid_for(n, WARPS_PER_CTA), WARPS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(n, states_d, weights_d, actions_d, scores_d,
@@ -937,6 +975,7 @@ int sb_select_action(SbHandle* h, int n, const uint8_t* states_d, const double* 
   return 0;
 }
 int sb_rollout_random(SbHandle* h, int n, uint8_t* states_d, int max_steps, int32_t* steps_d, uint64_t* chain_d, void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   if (use_warp_engine(h, WK_ROLLOUT_RANDOM, n)) {
     int shape = h->w_shape;
@@ -973,6 +1012,7 @@ int sb_set_option(SbHandle* h, const char* key, int value) {
 int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_first_d, const double* w_second_d,
                          const int32_t* idx_first_d, const int32_t* idx_second_d, int max_steps, int8_t* result_d, int32_t* steps_d,
                          void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (use_warp_engine(h, WK_ROLLOUT_HEUR, n)) {
@@ -1008,8 +1048,17 @@ int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_
   return 0;
 }
 int sb_accumulate_fitness(SbHandle* h, int n, const int8_t* result_d, const int32_t* idx_first_d, int32_t* counts_d, void* stream) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   k_accumulate_fitness<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, (const i8*)result_d, idx_first_d, counts_d);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int sb_count_aborted(SbHandle* h, int n, const uint8_t* states_d, const int8_t* result_d, int32_t* out_d, void* stream) {
+  DEV_GUARD(h);
+  if (n <= 0) return 0;
+  k_count_aborted<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(n, states_d, (const i8*)result_d, out_d);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1027,6 +1076,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 int sb_step_host(SbHandle* h, int n, uint8_t* states, const uint8_t* actions, int8_t* reward, uint8_t* done, uint8_t* err,
                  uint32_t* next_masks) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   size_t o_states = 0, o_act = al256((size_t)n * SB_STATE_BYTES), o_rew = o_act + al256(n), o_done = o_rew + al256(n),
          o_err = o_done + al256(n), o_mask = o_err + al256(n), total = o_mask + al256((size_t)n * SB_MASK_WORDS * 4);
@@ -1049,6 +1099,7 @@ int sb_step_host(SbHandle* h, int n, uint8_t* states, const uint8_t* actions, in
 
 int sb_rollout_random_host(SbHandle* h, int n, const uint64_t* seeds, const uint8_t* decks, int n_deck, const uint8_t* factions,
                            int max_steps, uint8_t* states_out, int32_t* steps_out, uint64_t* chain_out) {
+  DEV_GUARD(h);
   if (n <= 0) return 0;
   size_t o_states = 0, o_seed = al256((size_t)n * SB_STATE_BYTES), o_deck = o_seed + al256((size_t)n * 8),
          o_fac = o_deck + al256((size_t)2 * n_deck), o_steps = o_fac + 256, o_chain = o_steps + al256((size_t)n * 4),

@@ -4,6 +4,7 @@ torch is plumbing only (device memory, streams, torch.distributed); every rule, 
 computed by the CUDA kernels behind the C ABI (include/sb_b200.h).  No CPU path exists.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -42,8 +43,8 @@ class Engine:
         if rc != 0:
             msg = self.lib.sb_last_error(h).decode() if h else "sb_create failed"
             raise _lib.SbError("sb_create(%d) -> %d: %s" % (self.device.index, rc, msg))
-        self.h = h
-        torch.cuda.set_device(self.device)  # sb_create sets the stack-size limit on this device's primary context
+        self.h = h  # the caller's current device is left alone: every sb_* entry switches to the handle's device and back
+        self._default_decks = None
         self.sm_count = self.lib.sb_sm_count(h)
 
     def close(self):
@@ -90,8 +91,10 @@ class Engine:
         n = seeds.numel()
         seeds = self._dev(seeds.view(torch.int64) if seeds.dtype != torch.int64 else seeds, torch.int64)
         if decks is None:
-            decks = torch.tensor([deck_indices(d) for d in DEFAULT_DECKS], dtype=torch.uint8, device=self.device)
-            factions = torch.tensor(DEFAULT_FACTIONS, dtype=torch.uint8, device=self.device)
+            if self._default_decks is None:  # built once: two pageable H2D copies per call otherwise
+                self._default_decks = (torch.tensor([deck_indices(d) for d in DEFAULT_DECKS], dtype=torch.uint8, device=self.device),
+                                       torch.tensor(DEFAULT_FACTIONS, dtype=torch.uint8, device=self.device))
+            decks, factions = self._default_decks
         decks = self._dev(decks, torch.uint8)
         shared = 1 if decks.dim() == 2 else 0
         n_deck = decks.shape[-1]
@@ -210,6 +213,14 @@ class Engine:
             raise ValueError("at least one seat needs a weight table (expert-vs-expert games: expert_action + step)")
         w_first = None if w_first is None else self._dev(w_first, torch.float64)
         w_second = None if w_second is None else self._dev(w_second, torch.float64)
+        for w, idx in ((w_first, idx_first), (w_second, idx_second)):  # the kernels index these tables unchecked
+            if w is not None:
+                assert w.dim() == 2 and w.shape[1] == 10, "weight tables are f64[P, 10] (SB_N_FEATURES)"
+                if idx is None:
+                    assert w.shape[0] >= n
+                else:
+                    self._dev(idx, torch.int32)
+                    assert idx.numel() == n
         result = torch.empty(n, dtype=torch.int8, device=self.device)
         steps = torch.empty(n, dtype=torch.int32, device=self.device)
         self._check(self.lib.sb_rollout_heuristic(self.h, n, self._p(states), self._p(w_first), self._p(w_second),
@@ -222,6 +233,13 @@ class Engine:
         self._check(self.lib.sb_accumulate_fitness(self.h, n, self._p(result), self._p(idx_first), self._p(counts),
                                                    self._stream()), "sb_accumulate_fitness")
         return counts
+
+    def count_aborted(self, states, result, out=None):
+        """i32[2] += {aborted like the reference would (err 1..4), aborted by a limit of this engine (err 5..7)}"""
+        out = out if out is not None else torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._check(self.lib.sb_count_aborted(self.h, result.shape[0], self._p(states), self._p(result), self._p(out), self._stream()),
+                    "sb_count_aborted")
+        return out
 
     # ------------------------------------------------------------------ host-buffer (e2e) entry points
     def step_host(self, states_np, actions_np, want_masks=True):
@@ -258,7 +276,16 @@ class Engine:
 _engines = {}
 
 
-def get_engine(device=0):
+def get_engine(device=None):
+    """One engine per device; None = the caller's current CUDA device (LOCAL_RANK under torchrun once the launcher has
+    called torch.cuda.set_device), never a hard-wired device 0."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        lr = os.environ.get("LOCAL_RANK")
+        if device == 0 and lr is not None and torch.cuda.is_available():  # torchrun rank that never called set_device
+            device = int(lr) % torch.cuda.device_count()
+    if isinstance(device, torch.device):
+        device = device.index or 0
     if device not in _engines:
         _engines[device] = Engine(device)
     return _engines[device]

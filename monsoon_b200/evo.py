@@ -287,6 +287,8 @@ class FitnessEvaluator:
         self._eng = engine
         self._device = device
         self.last_counts = None
+        self.last_aborted = (0, 0)  # games of the last evaluation stopped (like the reference would / by a limit of this engine)
+        self.total_aborted = [0, 0]
 
     # -- plumbing
     def _engine(self):
@@ -376,6 +378,7 @@ class FitnessEvaluator:
         base_seed = int(getattr(self.config, "seed", 0) or 0)
         max_steps = int(self.config.max_turns)
         counts = torch.zeros((len(population), 3), dtype=torch.int32, device=dev)
+        aborted = torch.zeros(2, dtype=torch.int32, device=dev)
         for c0 in range(lo, hi, self.chunk_games):
             c1 = min(hi, c0 + self.chunk_games)
             gi = np.arange(c0, c1, dtype=np.int64)
@@ -393,18 +396,34 @@ class FitnessEvaluator:
             result, _steps = eng.rollout_heuristic(states, w, None if expert_second else w, idx_first, None if expert_second else idx_second,
                                                    max_steps=max_steps)
             eng.accumulate_fitness(result, idx_first, counts)
+            eng.count_aborted(states, result, aborted)
         if dist_on:
             dist.all_reduce(counts, op=dist.ReduceOp.SUM)  # integer counts: order-independent, bit-exact
+            dist.all_reduce(aborted, op=dist.ReduceOp.SUM)
+        ab = aborted.cpu().numpy()
+        self.last_aborted = (int(ab[0]), int(ab[1]))
+        self.total_aborted[0] += int(ab[0])
+        self.total_aborted[1] += int(ab[1])
+        if ab[1] * 100 > max(n_games, 1):  # scored as draws although the reference would have kept playing: say so
+            import warnings
+            warnings.warn("%d of %d games stopped at a capacity limit of the engine (SB_ERR_UNSUPPORTED/OVERFLOW/DEPTH) and were "
+                          "scored as draws" % (int(ab[1]), n_games))
         return counts.cpu().numpy().astype(np.int64)
 
     def get_stats(self):
         return {"total_games": self.total_games, "total_time": self.total_time,
                 "avg_time_per_game": self.total_time / max(self.total_games, 1),
-                "games_per_second": self.total_games / max(self.total_time, 1e-6)}
+                "games_per_second": self.total_games / max(self.total_time, 1e-6)}  # exactly the reference's keys (evo/fitness.py:230-240)
+
+    def get_aborted(self):
+        """games stopped early since the last reset_stats(): by an exception the reference raises too (scored as a draw there as
+        well, evo/fitness.py:208-210) / by a capacity limit of this engine (the reference would have kept playing)"""
+        return {"aborted_like_reference": self.total_aborted[0], "aborted_by_engine_limit": self.total_aborted[1]}
 
     def reset_stats(self):
         self.total_games = 0
         self.total_time = 0.0
+        self.total_aborted = [0, 0]
 
     def _update_hall_of_fame(self, population, fitness):  # evo/fitness.py:247-259
         pairs = sorted(zip(fitness, range(len(population))), key=lambda x: x[0], reverse=True)

@@ -38,7 +38,7 @@ def mask_to_actions(mask_words):
 class BatchedGames:
     """n independent games resident on one GPU."""
 
-    def __init__(self, seeds, decks=None, factions=None, device=0, engine=None):
+    def __init__(self, seeds, decks=None, factions=None, device=None, engine=None):
         self.eng = engine or get_engine(device)
         dev = self.eng.device
         self.seeds = torch.as_tensor(np.asarray(seeds, dtype=np.int64)).to(dev)
@@ -126,7 +126,7 @@ class _Env:
 class Game:
     """games/stormbound.py:121-250 `Game` (an AbstractGame): one game, state on the GPU."""
 
-    def __init__(self, seed=None, decks=None, factions=None, device=0, engine=None, _state=None):
+    def __init__(self, seed=None, decks=None, factions=None, device=None, engine=None, _state=None):
         self.eng = engine or get_engine(device)
         if seed is None:  # the reference seeds RandomState from OS entropy in this case (Q16)
             seed = int(np.random.SeedSequence().entropy & 0x7FFFFFFFFFFFFFFF)
@@ -214,7 +214,7 @@ class EvolutionaryStormbound:
     The reference keeps dealing from one RandomState; here deal number k of a game uses the stream key seed + k * 2^32.
     """
 
-    def __init__(self, seed=None, generation=0, deck_config=None, device=0, engine=None):
+    def __init__(self, seed=None, generation=0, deck_config=None, device=None, engine=None):
         from .evo import DeckEvolutionConfig
         self.eng = engine or get_engine(device)
         if seed is None:

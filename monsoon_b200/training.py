@@ -182,7 +182,7 @@ class Population:
 
     def __init__(self, config, engine=None, device=None):
         self.config = config
-        self.eng = engine or get_engine(device if device is not None else 0)
+        self.eng = engine or get_engine(device)  # None = the current CUDA device (LOCAL_RANK under torchrun)
         self.fitness_scores = []
         self.generation = 0
         self.w = self.s = None

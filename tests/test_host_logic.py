@@ -98,6 +98,12 @@ class OracleEngine:
             counts[i, 0 if r == 0 else 2 if r == 1 else 1] += 1
         return counts
 
+    def count_aborted(self, states, result, out):
+        for r, st in zip(result.tolist(), states.numpy()):
+            if r == -2:
+                out[1 if st[18] >= 5 else 0] += 1
+        return out
+
 
 def _deck_schedule():
     from monsoon_b200.evo import DeckEvolutionConfig
