@@ -123,9 +123,12 @@ SBD void random_deck(DeckRng& r, const u8* pool, int n_pool, const u8* original,
   py_sample(r, pool, n_pool, 12 - n_preserve, deck + n_preserve);
 }
 // pools: [5][POOL_W] card ids per faction (row 0 = NEUTRAL only), pool_n[5]; factions: per game [n][2] or one shared pair
+struct ArchParams { u8 arch[24]; u8 fac[2]; };  // the two archetype decks and their factions travel as kernel arguments
 __global__ void __launch_bounds__(128) k_generate_decks(int n, const unsigned long long* seeds, u32 generation, int mode, int n_preserve,
-                                                       double q, const u8* archetypes, const u8* factions, int factions_shared,
+                                                       double q, const ArchParams ap, const u8* factions_d, int factions_shared,
                                                        const u8* pools, const int* pool_n, u8* decks, u8* factions_out) {
+  const u8* archetypes = ap.arch;
+  const u8* factions = factions_shared ? ap.fac : factions_d;
   __shared__ u8 s_pool[5 * POOL_W];
   __shared__ int s_pn[5];
   __shared__ u8 s_arch[24];
@@ -855,17 +858,14 @@ int sb_generate_decks(SbHandle* h, int n, const uint64_t* seeds_d, uint32_t gene
     snprintf(h->err, sizeof h->err, "sb_generate_decks: bad mode/arguments");
     return -1;
   }
-  uint8_t host[32];
-  memset(host, 0, sizeof host);
-  if (archetypes) memcpy(host, archetypes, 24);
-  if (arch_factions) memcpy(host + 24, arch_factions, 2);
+  ArchParams ap;  // by value: no staging copy, no stream synchronisation inside the call
+  memset(&ap, 0, sizeof ap);
+  if (archetypes) memcpy(ap.arch, archetypes, 24);
+  if (arch_factions) memcpy(ap.fac, arch_factions, 2);
   cudaStream_t st = (cudaStream_t)stream;
-  CK(cudaMemcpyAsync(h->d_arch, host, 32, cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));  // `host` is a stack buffer
   const bool shared = factions_d == nullptr;
-  k_generate_decks<<<grid_for(n, 128), 128, 0, st>>>(n, (const unsigned long long*)seeds_d, generation, mode, n_preserve, q, h->d_arch,
-                                                   shared ? h->d_arch + 24 : factions_d, shared ? 1 : 0, h->d_pools, h->d_pool_n,
-                                                   decks_d, factions_out_d);
+  k_generate_decks<<<grid_for(n, 128), 128, 0, st>>>(n, (const unsigned long long*)seeds_d, generation, mode, n_preserve, q, ap,
+                                                   factions_d, shared ? 1 : 0, h->d_pools, h->d_pool_n, decks_d, factions_out_d);
   LAUNCH_CHECK();
   return 0;
 }

@@ -81,6 +81,78 @@ SBW_NI void w_unpack(WG* wg, const SbState* s) {
   }
 }
 
+// Stormbound.legal_actions (games/stormbound.py:528-557) STRAIGHT FROM THE PACKED RECORD, one lane per tile: the streaming
+// form of w_unpack + w_legal_mask for the record-in / mask-out API (sb_legal_mask), ~100 warp instructions per record instead
+// of ~600, so that the kernel is bound by HBM, not by issue.  m: 5 words, uniform result.  Returns the number of legal actions.
+SBW_FI int w_legal_mask_packed(const SbState* s, const DCard* cards, u32* m) {
+  W_SHARED(cards);
+  const int lo = s->local_order;
+  const SbPlayer& p = s->pl[lo];
+  const u32 occ = w_ballot([&](int l) -> bool { return l < SB_N_TILES && s->tile[l].card != 0; });
+#pragma unroll
+  for (int i = 0; i < SB_MASK_WORDS; i++) m[i] = 0;
+  const u32 fr = ~occ;
+  u32 empty16 = ((fr >> 16) & 0xFu) | (((fr >> 12) & 0xFu) << 4) | (((fr >> 8) & 0xFu) << 8) | (((fr >> 4) & 0xFu) << 12);
+  const int fl = p.front_line < 1 ? 1 : p.front_line;
+  empty16 &= fl > 4 ? 0u : (0xFFFFu >> ((fl - 1) * 4));
+  const int n_empty = w_popc(empty16);
+  const int nh = p.n_hand < SB_HAND_MAX ? p.n_hand : SB_HAND_MAX;
+  const int mana = p.mana;
+  int n_play = 0;
+#pragma unroll 1
+  for (int ci = 0; ci < nh; ci++) {
+    const DCard& c = cards[p.hand_card[ci]];
+    if (p.hand_cost[ci] > mana) continue;
+    if (c.kind != KIND_SPELL) {
+      const int a0 = 16 * ci;
+      m[a0 >> 5] |= empty16 << (a0 & 31);
+      n_play += n_empty;
+    } else if (!(c.flags & DCF_TARGET)) {
+      w_mask_set(m, 64 + 21 * ci); n_play++;
+    } else {  // board.get_targets(None, required_targets) on the packed tiles (board.py:147-204); pov = board.current_player
+      const int pov = s->current_order;
+      const int kind = c.t_ks & 3, side = c.t_ks >> 2;
+      const bool has_limit = c.t_limit >= 0;
+      const int limit = c.t_limit;
+      const u32 want_types = c.t_types, bad_types = (u32)c.t_xtypes | ((c.flags & DCF_TNONHERO) ? (1u << UT_HERO) : 0u);
+      const u32 want_status = c.t_status, bad_status = c.t_xstatus;
+      u32 tm = w_ballot([&](int l) -> bool {
+        if (l >= SB_N_TILES) return false;
+        const SbTile t = s->tile[l];
+        if (!t.card || t.strength <= 0) return false;
+        const bool is_struct = (t.flags & SB_TF_STRUCTURE) != 0;
+        if (kind == TK_UNIT ? is_struct : (kind == TK_STRUCTURE ? !is_struct : false)) return false;
+        const bool mine = ((t.flags & SB_TF_OWNER) ? 1 : 0) == pov;
+        if (side == TS_FRIENDLY ? !mine : (side == TS_ENEMY ? mine : false)) return false;
+        if (has_limit && t.strength > limit) return false;
+        if (!is_struct) {
+          if (want_types | bad_types) {
+            const u32 types = cards[t.card].types;
+            if ((want_types && !(types & want_types)) || (types & bad_types)) return false;
+          }
+          if (want_status | bad_status) {
+            u32 have = 0;
+#pragma unroll
+            for (int k = 0; k < 5; k++) have |= (((t.status >> (SB_ST_BITS * k)) & 63u) ? 1u : 0u) << k;
+            if ((want_status && !(have & want_status)) || (have & bad_status)) return false;
+          }
+        }
+        return true;
+      });
+#pragma unroll 1
+      while (tm) {
+        const int tile = w_ffs(tm) - 1;
+        tm &= tm - 1;
+        w_mask_set(m, 65 + 21 * ci + (4 - (tile >> 2)) * 4 + (tile & 3)); n_play++;
+      }
+    }
+  }
+  int n = n_play;
+  if (p.flags & SB_PF_REPLACABLE) for (int ci = 0; ci < nh; ci++) { w_mask_set(m, 148 + ci); n++; }
+  if (n_play == 0) { w_mask_set(m, 155); n++; }
+  return n;
+}
+
 // one memory tree in pre-order (explicit stack in scratch; key = owning temple tile, or 0x80 | packed index of the parent copy)
 SBW_NI void w_pack_mem(WG* wg, SbState* s, int root, int root_key, int& nm) {
   W_SHARED(wg);

@@ -48,7 +48,7 @@ __device__ __forceinline__ int kw_next_game(int* queue, int fallback) {  // pers
 // CTA play their non-PASS actions round by round (CTA-wide vote per round) and then their PASS together, so the warps of
 // an SM walk the same functions at the same time and share the instruction-cache lines they fetch (the unsynchronised
 // kernel spends 70-85 % of its stall samples waiting for instructions: profiles/r2_summary.md).
-template <int WPC, int MINB, bool SYNC>
+template <int WPC, int MINB, int SYNC>
 __global__ void __launch_bounds__(WPC * 32, MINB) kw_rollout_random(int n, u8* states, int max_steps, int* steps_out, unsigned long long* chain,
                                                                      const DCard* cards, const double* wt, int* queue) {
   __shared__ DCard s_cards[SBC_COUNT];
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) kw_rollout_random(int n, u8* s
   wg->cards = s_cards; wg->wt = wt;
   const bool digest = chain != nullptr;
   int gi = blockIdx.x * WPC + warp;
-  if (!SYNC) {
+  if (SYNC == 0) {
 #pragma unroll 1
     for (;;) {
       gi = kw_next_game(queue, gi);
@@ -121,7 +121,9 @@ __global__ void __launch_bounds__(WPC * 32, MINB) kw_rollout_random(int n, u8* s
           a = w_pick_action(wg);
           if (a == SB_ACTION_PASS) { at_pass = true; a = -1; }
         }
-        if (!__syncthreads_or(a >= 0)) break;
+        if (SYNC == 2) {  // two barriers per turn: every warp plays ALL its non-PASS actions of the turn, then everybody's PASS
+          if (a < 0) { __syncthreads(); break; }
+        } else if (!__syncthreads_or(a >= 0)) break;
         if (a >= 0) {
           w_game_step(wg, a);
           w_end_of_step(wg);
@@ -173,6 +175,34 @@ __global__ void __launch_bounds__(WPC * 32) kw_step(int n, u8* states, const u8*
       w_legal_mask(wg);
       if (lane < SB_MASK_WORDS) next_masks[(size_t)gi * SB_MASK_WORDS + lane] = wg->lm[lane];
     }
+    __syncwarp();
+  }
+}
+
+// sb_legal_mask as a STREAMING kernel: the mask is computed straight from the packed record (w_legal_mask_packed, one lane per
+// tile), ~100 warp instructions per record, so the kernel is bound by the record stream itself: every warp keeps the NEXT
+// record's 512 bytes in flight (one 128-bit load per lane, issued before the current record is processed) and the persistent
+// grid covers the chip with 2,048 threads per SM.  Algorithmic bytes: 512 in + 20 out per record.
+template <int WPC>
+__global__ void __launch_bounds__(WPC * 32, 2048 / (WPC * 32)) kw_legal_mask_direct(int n, const u8* states, u32* masks, const DCard* cards) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  __shared__ __align__(16) SbState s_img[WPC];
+  kw_stage_cards(s_cards, cards);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stride = gridDim.x * WPC;
+  int gi = blockIdx.x * WPC + warp;
+  uint4 nxt = make_uint4(0, 0, 0, 0);
+  if (gi < n) nxt = __ldg(reinterpret_cast<const uint4*>(states + (size_t)gi * SB_STATE_BYTES) + lane);
+#pragma unroll 1
+  for (; gi < n; gi += stride) {
+    const uint4 cur = nxt;
+    if (gi + stride < n) nxt = __ldg(reinterpret_cast<const uint4*>(states + (size_t)(gi + stride) * SB_STATE_BYTES) + lane);
+    reinterpret_cast<uint4*>(&s_img[warp])[lane] = cur;
+    __syncwarp();
+    u32 m[SB_MASK_WORDS];
+    w_legal_mask_packed(&s_img[warp], s_cards, m);
+    const u32 v = lane == 0 ? m[0] : lane == 1 ? m[1] : lane == 2 ? m[2] : lane == 3 ? m[3] : m[4];
+    if (lane < SB_MASK_WORDS) masks[(size_t)gi * SB_MASK_WORDS + lane] = v;
     __syncwarp();
   }
 }
@@ -320,15 +350,17 @@ int sbw_wg_bytes(void) { return (int)sizeof(WG); }
 
 cudaError_t sbw_init(void) {
   { const char* e = getenv("SBW_CARVEOUT"); if (e) g_carveout = atoi(e); }
-  W_TRY((set_smem(kw_rollout_random<4, 8, false>, 4 * W_SLOT_BYTES)));
-  W_TRY((set_smem(kw_rollout_random<8, 4, false>, 8 * W_SLOT_BYTES)));
-  W_TRY((set_smem(kw_rollout_random<8, 8, false>, 8 * W_SLOT_BYTES)));
-  W_TRY((set_smem(kw_rollout_random<8, 4, true>, 8 * W_SLOT_BYTES)));
-  W_TRY((set_smem(kw_rollout_random<16, 2, true>, 16 * W_SLOT_BYTES)));
-  W_TRY((set_smem(kw_rollout_random<32, 1, true>, 32 * W_SLOT_BYTES)));
-  W_TRY((set_smem(kw_rollout_random<32, 2, true>, 32 * W_SLOT_BYTES)));
-  W_TRY((set_smem(kw_rollout_random<28, 1, true>, 28 * W_SLOT_BYTES)));
-  W_TRY((set_smem(kw_rollout_random<14, 2, true>, 14 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<4, 8, 0>, 4 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<8, 4, 0>, 8 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<8, 8, 0>, 8 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<8, 4, 1>, 8 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<16, 2, 1>, 16 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<32, 1, 1>, 32 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<32, 2, 1>, 32 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<28, 1, 1>, 28 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<14, 2, 1>, 14 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<32, 1, 2>, 32 * W_SLOT_BYTES)));
+  W_TRY((set_smem(kw_rollout_random<16, 2, 2>, 16 * W_SLOT_BYTES)));
   W_TRY(set_smem(kw_step<8>, 8 * W_SLOT_BYTES));
   W_TRY(set_smem(kw_query<8, 0>, 8 * W_SLOT_BYTES));
   W_TRY(set_smem(kw_query<8, 1>, 8 * W_SLOT_BYTES));
@@ -342,11 +374,12 @@ cudaError_t sbw_init(void) {
 
 // shape: 0 = 8-warp CTAs x 4 per SM (1,024 threads, 64 registers), 1 = 4-warp CTAs x 8 per SM (same occupancy, finer CTAs),
 //        2 = 8-warp CTAs x 8 per SM (2,048 threads, 32 registers); turn-synchronous CTAs: 3 = 8 warps x 4, 4 = 16 warps x 2,
-//        5 = 32 warps x 1, 6 = 32 warps x 2 (32 registers), 7 = 28 warps x 1 (4,096 games = 147 CTAs: every SM busy), 8 = 14 warps x 2
+//        5 = 32 warps x 1, 6 = 32 warps x 2 (32 registers), 7 = 28 warps x 1 (4,096 games = 147 CTAs: every SM busy), 8 = 14 warps x 2;
+//        two barriers per turn instead of one vote per action: 9 = 32 warps x 1, 10 = 16 warps x 2
 void sbw_rollout_random(const SbwCtx* c, int n, uint8_t* states, int max_steps, int32_t* steps, uint64_t* chain, int shape, int grid_override,
                         cudaStream_t st) {
-  static const int WPCS[9] = {8, 4, 8, 8, 16, 32, 32, 28, 14}, PER_SM[9] = {4, 8, 8, 4, 2, 1, 2, 1, 2};
-  if (shape < 0 || shape > 8) shape = 0;
+  static const int WPCS[11] = {8, 4, 8, 8, 16, 32, 32, 28, 14, 32, 16}, PER_SM[11] = {4, 8, 8, 4, 2, 1, 2, 1, 2, 1, 2};
+  if (shape < 0 || shape > 10) shape = 0;
   const int wpc = WPCS[shape], per_sm = PER_SM[shape];
   const int resident = c->sm_count * per_sm;  // CTAs in flight
   const int full = grid_for(n, wpc);
@@ -360,15 +393,17 @@ void sbw_rollout_random(const SbwCtx* c, int n, uint8_t* states, int max_steps, 
   unsigned long long* ch = (unsigned long long*)chain;
 #define RR(W, B, S) kw_rollout_random<W, B, S><<<grid, W * 32, W * W_SLOT_BYTES, st>>>(n, states, max_steps, steps, ch, c->d_cards, c->d_wt, q)
   switch (shape) {
-    case 0: RR(8, 4, false); break;
-    case 1: RR(4, 8, false); break;
-    case 2: RR(8, 8, false); break;
-    case 3: RR(8, 4, true); break;
-    case 4: RR(16, 2, true); break;
-    case 5: RR(32, 1, true); break;
-    case 6: RR(32, 2, true); break;
-    case 7: RR(28, 1, true); break;
-    default: RR(14, 2, true); break;
+    case 0: RR(8, 4, 0); break;
+    case 1: RR(4, 8, 0); break;
+    case 2: RR(8, 8, 0); break;
+    case 3: RR(8, 4, 1); break;
+    case 4: RR(16, 2, 1); break;
+    case 5: RR(32, 1, 1); break;
+    case 6: RR(32, 2, 1); break;
+    case 7: RR(28, 1, 1); break;
+    case 8: RR(14, 2, 1); break;
+    case 9: RR(32, 1, 2); break;
+    default: RR(16, 2, 2); break;
   }
 #undef RR
 }
@@ -381,7 +416,8 @@ void sbw_step(const SbwCtx* c, int n, uint8_t* states, const uint8_t* actions, i
   kw_step<8><<<query_grid(c, n, 8), 256, 8 * W_SLOT_BYTES, st>>>(n, states, actions, (i8*)reward, done, err, next_masks, c->d_cards, c->d_wt);
 }
 void sbw_legal_mask(const SbwCtx* c, int n, const uint8_t* states, uint32_t* masks, cudaStream_t st) {
-  kw_query<8, 0><<<query_grid(c, n, 8), 256, 8 * W_SLOT_BYTES, st>>>(n, (u8*)states, masks, nullptr, c->d_cards, c->d_wt);
+  const int full = grid_for(n, 8), cap = c->sm_count * 8;  // persistent grid: 8 CTAs of 8 warps per SM
+  kw_legal_mask_direct<8><<<full < cap ? full : cap, 256, 0, st>>>(n, states, masks, c->d_cards);
 }
 void sbw_observe(const SbwCtx* c, int n, const uint8_t* states, int32_t* obs, uint8_t* err, cudaStream_t st) {
   kw_query<8, 1><<<query_grid(c, n, 8), 256, 8 * W_SLOT_BYTES, st>>>(n, (u8*)states, obs, err, c->d_cards, c->d_wt);

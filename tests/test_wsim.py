@@ -59,12 +59,13 @@ def test_every_step_equals_oracle(oracle, wsim):
     z = load("randdeck_chain.npz")
     import ref_harness as h
     for i, st in _games(z, oracle):
-        if i >= 300:
+        if i >= 400:
             break
         sw, seed = st.copy(), int(z["seeds"][i])
         for k in range(400):
             m = oracle.legal_mask(st)
             assert np.array_equal(m, wsim.legal_mask(sw)), (seed, k)
+            assert np.array_equal(m, wsim.legal_mask_packed(sw)), (seed, k)  # the streaming form (no unpack)
             legal = [a for a in range(156) if m[a >> 5] >> (a & 31) & 1]
             a = legal[h.agent_pick(seed, k, len(legal))]
             oracle.step(st, a)

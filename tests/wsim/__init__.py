@@ -50,6 +50,12 @@ def legal_mask(st, L=None):
     return m
 
 
+def legal_mask_packed(st):
+    m = np.zeros(5, dtype=np.uint32)
+    lib().wsim_legal_mask_packed(_p(st), _p(m))
+    return m
+
+
 def step(st, action, L=None):
     (L or lib()).wsim_step(_p(st), int(action))
 

@@ -30,6 +30,10 @@ void wsim_legal_mask(const uint8_t* state, uint32_t* mask) {
   w_legal_mask(&wg);
   for (int i = 0; i < SB_MASK_WORDS; i++) mask[i] = wg.lm[i];
 }
+void wsim_legal_mask_packed(const uint8_t* state, uint32_t* mask) {  // the streaming form: no unpack
+  init_once();
+  w_legal_mask_packed((const SbState*)state, g_cards, mask);
+}
 void wsim_step(uint8_t* state, int action) {
   init_once();
   WG wg; wg_init(&wg);
