@@ -677,9 +677,9 @@ static inline bool use_warp_engine(const SbHandle* h, int kind, int n) {
   switch (kind) {
     case WK_ROLLOUT_RANDOM: return n <= h->sm_count * 32;   // one wave of 32-warp CTAs (4,096 games: 85 against 73 M env-steps/s)
     case WK_STEP: return n <= 8192;                          // 4,096 games: 0.077 against 0.143 ms; 65,536: 0.89 against 0.37 ms
-    case WK_LEGAL_MASK: return true;                         // 553 against 409 GB/s at 65,536 records, 822 against 664 at 1 M
-    case WK_OBSERVE: return true;                            // 686 against 380 GB/s at 65,536 records
-    case WK_FEATURES: return n <= 65536;
+    case WK_LEGAL_MASK: return true;                         // streaming kernel: 1,843 against 651 GB/s at 1 M records
+    case WK_OBSERVE: return true;                            // streaming kernel: 1,626 against 382 GB/s at 65,536 records
+    case WK_FEATURES: return n <= 65536;                     // 407 against 355 GB/s at 65,536 records; 512 against 650 at 1 M
     case WK_EXPERT: return n <= 16384;
     default: return false;                                   // heuristic agent: lane per candidate wins 3.5x
   }

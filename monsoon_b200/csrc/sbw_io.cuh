@@ -153,6 +153,102 @@ SBW_FI int w_legal_mask_packed(const SbState* s, const DCard* cards, u32* m) {
   return n;
 }
 
+// Stormbound.get_observation (games/stormbound.py:400-526) STRAIGHT FROM THE PACKED RECORD into a 540-int buffer `ob`
+// (shared memory on the GPU: the kernel then streams it out with 128-bit stores).  One lane per tile / hand card / deck card /
+// history entry; the deck's sorted(key=(cost, card_id)) is a rank computed by every deck lane against all deck cards.
+// Returns 0 or SB_ERR_OBS_ID (Q12).  Pure data movement: ~350 warp instructions for 512 B in, 2,160 B out.
+SBW_FI int w_packed_card_strength(const SbState* s, const DCard* cards, int order, int in_deck, int idx, int card, int flags) {
+  if (!(flags & SB_CF_OBJ)) return cards[card].strength;
+  const u8* x = s->ext;  // board-instance card record (cards/b305.py:41-45): live link to a tile, or the frozen strength
+  const int no = x[91] < NOBJ_PACKED ? x[91] : NOBJ_PACKED;
+  const int key = (order << 7) | (in_deck << 6) | idx;
+#pragma unroll 1
+  for (int i = 0; i < no; i++) {
+    const u8* r = x + 92 + 4 * i;
+    if (r[0] != key) continue;
+    if (r[1] != 0xFF) return s->tile[r[1] < SB_N_TILES ? r[1] : 0].strength;
+    return (i16)(r[2] | (r[3] << 8));
+  }
+  return 0;  // w_unpack leaves link = -1, xstr = 0 for a record that did not fit ext
+}
+SBW_FI int w_observe_packed(const SbState* s, const DCard* cards, int* ob) {
+  W_SHARED(cards);
+  const int lo = s->local_order;
+  const SbPlayer& L = s->pl[lo];
+  const SbPlayer& R = s->pl[1 - lo];
+  const int sign = s->player_sign * 99999;
+  FOR_LANES(l) {
+#pragma unroll 1
+    for (int i = l; i < SB_OBS_INTS; i += 32) {
+      const int layer = i / 20, row = (i % 20) >> 2;
+      int v = -1;
+      if (layer == 13) v = L.mana; else if (layer == 14) v = L.base; else if (layer == 15) v = L.faction;
+      else if (layer == 22) v = R.mana; else if (layer == 23) v = R.base; else if (layer == 24) v = R.faction;
+      else if (layer == 25) v = sign;
+      else if (row == 4) { if (layer == 6) v = 32767; else if (layer >= 7 && layer <= 12) v = 32768; else if (layer == 26) v = 32769; }
+      ob[i] = v;
+    }
+  } END_LANES
+  const int nh = L.n_hand < SB_HAND_MAX ? L.n_hand : SB_HAND_MAX, nd = L.n_deck < SB_DECK_MAX ? L.n_deck : SB_DECK_MAX;
+  const int hn = s->hist_n < 4 ? s->hist_n : 4;
+  u32 bad = 0;
+  FOR_LANES(l) {
+    if (l < SB_N_TILES) {  // board layers 0-5 (own) / 16-21 (enemy)
+      const SbTile t = s->tile[l];
+      if (t.card) {
+        const DCard& d = cards[t.card];
+        const int base = (((t.flags & SB_TF_OWNER) ? 1 : 0) == lo ? 0 : 16) * 20 + l;
+        if (!(t.flags & SB_TF_STRUCTURE)) {
+          const u32 w = t.status;
+          ob[base] = d.obs_id; ob[base + 20] = t.strength; ob[base + 40] = d.movement;
+          ob[base + 60] = (((w >> (SB_ST_BITS * SB_ST_VITALIZED)) & 63u) ? 1 : 0) | (((w >> (SB_ST_BITS * SB_ST_POISONED)) & 63u) ? 2 : 0) |
+                          (((w >> (SB_ST_BITS * SB_ST_CONFUSED)) & 63u) ? 4 : 0) | (((w >> (SB_ST_BITS * SB_ST_FROZEN)) & 63u) ? 8 : 0) |
+                          (((w >> (SB_ST_BITS * SB_ST_DISABLED)) & 63u) ? 16 : 0);
+        } else { ob[base + 80] = d.obs_id; ob[base + 100] = t.strength; }
+      }
+    } else if (l < SB_N_TILES + 4) {  // hand, layer 6
+      const int i = l - SB_N_TILES;
+      if (i < nh) {
+        const int card = L.hand_card[i];
+        const DCard& d = cards[card];
+        int* o = ob + 6 * 20 + i * 4;
+        o[0] = d.obs_id; o[1] = L.hand_cost[i];
+        o[2] = d.kind == KIND_SPELL ? -1 : w_packed_card_strength(s, cards, lo, 0, i, card, L.hand_flags[i]);
+        o[3] = d.kind == KIND_UNIT ? d.movement : -1;
+      }
+    } else if (l < SB_N_TILES + 8) {  // history, layer 26: the last four plays, oldest first, right-aligned
+      const int i = l - SB_N_TILES - 4;
+      const int h = i - (4 - hn);
+      if (h >= 0) { ob[26 * 20 + i * 4] = s->hist_owner[h] ? -99999 : 99999; ob[26 * 20 + i * 4 + 1] = cards[s->hist_card[h]].obs_id; }
+    }
+  } END_LANES
+  FOR_LANES(l) {  // deck, layers 7-12: position = rank under the stable order (cost, card id)
+    if (l < nd) {
+      const int card = L.deck_card[l], cost = L.deck_cost[l];
+      int rank = 0;
+#pragma unroll 1
+      for (int j = 0; j < nd; j++) {
+        const int cj = L.deck_cost[j], kj = L.deck_card[j];
+        rank += (cj < cost || (cj == cost && (kj < card || (kj == card && j < l)))) ? 1 : 0;
+      }
+      const DCard& d = cards[card];
+      int* o = ob + (7 + (rank >> 2)) * 20 + (rank & 3) * 4;
+      o[0] = d.obs_id; o[1] = cost;
+      o[2] = d.kind == KIND_SPELL ? -1 : w_packed_card_strength(s, cards, lo, 1, l, card, L.deck_flags[l]);
+      o[3] = d.kind == KIND_UNIT ? d.movement : -1;
+    }
+  } END_LANES
+  bad = w_ballot([&](int l) -> bool {  // int(card) raises for UP01-03 on the board, in the hand, the deck or the history (Q12)
+    bool b = false;
+    if (l < SB_N_TILES) { const int c = s->tile[l].card; b = c && cards[c].obs_id == -32768; }
+    if (l < nd) b = b || cards[L.deck_card[l]].obs_id == -32768;
+    if (l < nh) b = b || cards[L.hand_card[l]].obs_id == -32768;
+    if (l < hn) b = b || cards[s->hist_card[l]].obs_id == -32768;
+    return b;
+  });
+  return bad ? SB_ERR_OBS_ID : 0;
+}
+
 // one memory tree in pre-order (explicit stack in scratch; key = owning temple tile, or 0x80 | packed index of the parent copy)
 SBW_NI void w_pack_mem(WG* wg, SbState* s, int root, int root_key, int& nm) {
   W_SHARED(wg);
@@ -399,6 +495,87 @@ SBW_FI double w_score_delta(const double* w, const double* fc, const double* fn)
   const double eff = d_sub(fn[0], fc[0]);
   const double rp = eff < -0.3 ? d_mul(eff < 0.0 ? -eff : eff, 0.2) : 0.0;
   return d_sub(d_sub(-d, d), rp);
+}
+
+// The ten StateFeatures STRAIGHT FROM THE PACKED RECORD (streaming form of w_unpack + w_features for sb_features): the same
+// arithmetic in the same order (ascending tiles for the two FP64 sums), reading the 8-byte tile records of the staging image.
+SBW_FI int w_features_packed(const SbState* s, const DCard* cards, double* f) {
+  W_SHARED(cards);
+  const int lo = s->local_order;
+  const SbPlayer& L = s->pl[lo];
+  const SbPlayer& R = s->pl[1 - lo];
+  const double m = L.mana != -1 ? (double)L.mana : 0.0;
+  const double hl = L.base != -1 ? (double)L.base : 20.0;
+  const double hr = R.base != -1 ? (double)R.base : 20.0;
+  double est = d_add(m, 2.0);
+  if (est < 3.0) est = 3.0;
+  if (est > 10.0) est = 10.0;
+  f[0] = w_clip01(d_sub(1.0, d_div(m, est)));
+  f[1] = d_sub(hl, hr);
+  int sl = 0, sr = 0, nl = 0, nr = 0, nsl = 0, nsr = 0, minl = 99, maxr = -1;
+  double threat = 0.0, prot = 0.0;
+  u32 occ = w_ballot([&](int l) -> bool { return l < SB_N_TILES && s->tile[l].card != 0; });
+#pragma unroll 1
+  while (occ) {
+    const int t = w_ffs(occ) - 1;
+    occ &= occ - 1;
+    const SbTile tl = s->tile[t];
+    const int y = t >> 2, str = tl.strength;
+    const bool counted = str != -1;
+    const bool is_struct = (tl.flags & SB_TF_STRUCTURE) != 0;
+    if (((tl.flags & SB_TF_OWNER) ? 1 : 0) == lo) {
+      if (!is_struct) { nl++; if (y < minl) minl = y; } else nsl++;
+      if (counted) { sl += str; prot = d_add(prot, d_mul((double)str, w_fifths(5 - y))); }
+    } else {
+      if (!is_struct) {
+        nr++; if (y > maxr) maxr = y;
+        if (counted) threat = d_add(threat, d_mul((double)str, w_fifths(y + 1)));
+      } else nsr++;
+      if (counted) sr += str;
+    }
+  }
+  const int tot = sl + sr;
+  f[2] = tot == 0 ? 0.0 : d_div((double)(sl - sr), (double)tot);
+  f[3] = (nl == 0 && nr == 0) ? 0.0 : d_mul((double)((nr ? maxr : 0) - (nl ? minl : 4)), 0.25);
+  f[4] = (double)(sl - sr);
+  f[5] = (double)(nl - nr);
+  f[6] = (double)(nsl - nsr);
+  f[7] = threat;
+  f[8] = prot;
+  const int nh = L.n_hand < SB_HAND_MAX ? L.n_hand : SB_HAND_MAX, nd = L.n_deck < SB_DECK_MAX ? L.n_deck : SB_DECK_MAX;
+  const int hn = s->hist_n < 4 ? s->hist_n : 4;
+  int playable = 0, valid = 0;
+  double total = 0.0;
+#pragma unroll 1
+  for (int i = 0; i < nh; i++) {
+    const int card = L.hand_card[i];
+    const DCard& c = cards[card];
+    if (c.obs_id == -1 || c.obs_id == 32767) continue;
+    const int cost = L.hand_cost[i];
+    int str = c.kind == KIND_SPELL ? 0 : w_packed_card_strength(s, cards, lo, 0, i, card, L.hand_flags[i]);
+    if (str == -1) str = 0;
+    valid++;
+    if (cost > 0) {
+      total = d_add(total, d_div((double)str, (double)cost));
+      if ((double)cost <= m) playable++;
+    }
+  }
+  if (valid == 0) f[9] = 0.0;
+  else {
+    double playability, avg;
+    if (valid == 3) { playability = d_div((double)playable, 3.0); avg = d_div(total, 3.0); }
+    else { const double inv = valid == 1 ? 1.0 : valid == 2 ? 0.5 : 0.25; playability = d_mul((double)playable, inv); avg = d_mul(total, inv); }
+    f[9] = d_mul(d_add(playability, w_clip01(d_div(avg, 3.0))), 0.5);
+  }
+  const u32 bad = w_ballot([&](int l) -> bool {
+    bool b = false;
+    if (l < SB_N_TILES) { const int c = s->tile[l].card; b = c && cards[c].obs_id == -32768; }
+    if (l < nd) b = b || cards[L.deck_card[l]].obs_id == -32768;
+    if (l < nh) b = b || cards[L.hand_card[l]].obs_id == -32768;
+    if (l < hn) b = b || cards[s->hist_card[l]].obs_id == -32768;
+    return b;
+  });
+  return bad ? SB_ERR_OBS_ID : 0;
 }
 
 // ---------------------------------------------------------------- observation (games/stormbound.py:400-526)

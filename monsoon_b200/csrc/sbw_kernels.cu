@@ -179,14 +179,17 @@ __global__ void __launch_bounds__(WPC * 32) kw_step(int n, u8* states, const u8*
   }
 }
 
-// sb_legal_mask as a STREAMING kernel: the mask is computed straight from the packed record (w_legal_mask_packed, one lane per
-// tile), ~100 warp instructions per record, so the kernel is bound by the record stream itself: every warp keeps the NEXT
-// record's 512 bytes in flight (one 128-bit load per lane, issued before the current record is processed) and the persistent
-// grid covers the chip with 2,048 threads per SM.  Algorithmic bytes: 512 in + 20 out per record.
-template <int WPC>
-__global__ void __launch_bounds__(WPC * 32, 2048 / (WPC * 32)) kw_legal_mask_direct(int n, const u8* states, u32* masks, const DCard* cards) {
+// The record-in / result-out queries as STREAMING kernels: legal mask (MODE 0), observation (1) and features (2) are computed
+// straight from the packed record (w_*_packed, one lane per tile / card), 250-450 warp instructions per record instead of the
+// 600-1,400 of unpack + query, so that the kernels run on the record stream instead of the issue slots.  Every warp keeps the
+// NEXT record's 512 bytes in flight (one 128-bit load per lane, issued before the current record is processed); the
+// observation is assembled in shared memory and leaves as 135 coalesced 128-bit stores.  Persistent grid, 2,048 threads per SM.
+// Algorithmic bytes per record: 512 in + 20 / 2,160 / 80 out.
+template <int WPC, int MODE>
+__global__ void __launch_bounds__(WPC * 32, 2048 / (WPC * 32)) kw_stream(int n, const u8* states, void* out, u8* err, const DCard* cards) {
   __shared__ DCard s_cards[SBC_COUNT];
   __shared__ __align__(16) SbState s_img[WPC];
+  __shared__ __align__(16) int s_out[MODE == 1 ? WPC * SB_OBS_INTS : (MODE == 2 ? WPC * 2 * SB_N_FEATURES : 4)];
   kw_stage_cards(s_cards, cards);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stride = gridDim.x * WPC;
@@ -199,10 +202,26 @@ __global__ void __launch_bounds__(WPC * 32, 2048 / (WPC * 32)) kw_legal_mask_dir
     if (gi + stride < n) nxt = __ldg(reinterpret_cast<const uint4*>(states + (size_t)(gi + stride) * SB_STATE_BYTES) + lane);
     reinterpret_cast<uint4*>(&s_img[warp])[lane] = cur;
     __syncwarp();
-    u32 m[SB_MASK_WORDS];
-    w_legal_mask_packed(&s_img[warp], s_cards, m);
-    const u32 v = lane == 0 ? m[0] : lane == 1 ? m[1] : lane == 2 ? m[2] : lane == 3 ? m[3] : m[4];
-    if (lane < SB_MASK_WORDS) masks[(size_t)gi * SB_MASK_WORDS + lane] = v;
+    if (MODE == 0) {
+      u32 m[SB_MASK_WORDS];
+      w_legal_mask_packed(&s_img[warp], s_cards, m);
+      const u32 v = lane == 0 ? m[0] : lane == 1 ? m[1] : lane == 2 ? m[2] : lane == 3 ? m[3] : m[4];
+      if (lane < SB_MASK_WORDS) reinterpret_cast<u32*>(out)[(size_t)gi * SB_MASK_WORDS + lane] = v;
+    } else if (MODE == 1) {
+      int* ob = s_out + warp * SB_OBS_INTS;
+      const int e = w_observe_packed(&s_img[warp], s_cards, ob);
+      uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<int*>(out) + (size_t)gi * SB_OBS_INTS);
+      const uint4* src = reinterpret_cast<const uint4*>(ob);
+#pragma unroll
+      for (int i = lane; i < SB_OBS_INTS / 4; i += 32) dst[i] = src[i];
+      if (err && lane == 0) err[gi] = (u8)e;
+    } else {
+      double* f = reinterpret_cast<double*>(s_out) + warp * SB_N_FEATURES;
+      const int e = w_features_packed(&s_img[warp], s_cards, f);
+      __syncwarp();
+      if (lane < SB_N_FEATURES) reinterpret_cast<double*>(out)[(size_t)gi * SB_N_FEATURES + lane] = f[lane];
+      if (err && lane == 0) err[gi] = (u8)e;
+    }
     __syncwarp();
   }
 }
@@ -362,9 +381,6 @@ cudaError_t sbw_init(void) {
   W_TRY((set_smem(kw_rollout_random<32, 1, 2>, 32 * W_SLOT_BYTES)));
   W_TRY((set_smem(kw_rollout_random<16, 2, 2>, 16 * W_SLOT_BYTES)));
   W_TRY(set_smem(kw_step<8>, 8 * W_SLOT_BYTES));
-  W_TRY(set_smem(kw_query<8, 0>, 8 * W_SLOT_BYTES));
-  W_TRY(set_smem(kw_query<8, 1>, 8 * W_SLOT_BYTES));
-  W_TRY(set_smem(kw_query<8, 2>, 8 * W_SLOT_BYTES));
   W_TRY(set_smem(kw_query<8, 3>, 8 * W_SLOT_BYTES));
   W_TRY(set_smem(kw_select_action<4>, 4 * W_HSLOT_BYTES));
   W_TRY(set_smem(kw_rollout_heuristic<4, 8>, 4 * W_HSLOT_BYTES));
@@ -417,13 +433,15 @@ void sbw_step(const SbwCtx* c, int n, uint8_t* states, const uint8_t* actions, i
 }
 void sbw_legal_mask(const SbwCtx* c, int n, const uint8_t* states, uint32_t* masks, cudaStream_t st) {
   const int full = grid_for(n, 8), cap = c->sm_count * 8;  // persistent grid: 8 CTAs of 8 warps per SM
-  kw_legal_mask_direct<8><<<full < cap ? full : cap, 256, 0, st>>>(n, states, masks, c->d_cards);
+  kw_stream<8, 0><<<full < cap ? full : cap, 256, 0, st>>>(n, states, masks, nullptr, c->d_cards);
 }
 void sbw_observe(const SbwCtx* c, int n, const uint8_t* states, int32_t* obs, uint8_t* err, cudaStream_t st) {
-  kw_query<8, 1><<<query_grid(c, n, 8), 256, 8 * W_SLOT_BYTES, st>>>(n, (u8*)states, obs, err, c->d_cards, c->d_wt);
+  const int full = grid_for(n, 8), cap = c->sm_count * 8;
+  kw_stream<8, 1><<<full < cap ? full : cap, 256, 0, st>>>(n, states, obs, err, c->d_cards);
 }
 void sbw_features(const SbwCtx* c, int n, const uint8_t* states, double* feat, uint8_t* err, cudaStream_t st) {
-  kw_query<8, 2><<<query_grid(c, n, 8), 256, 8 * W_SLOT_BYTES, st>>>(n, (u8*)states, feat, err, c->d_cards, c->d_wt);
+  const int full = grid_for(n, 8), cap = c->sm_count * 8;
+  kw_stream<8, 2><<<full < cap ? full : cap, 256, 0, st>>>(n, states, feat, err, c->d_cards);
 }
 void sbw_expert_action(const SbwCtx* c, int n, uint8_t* states, uint8_t* actions, cudaStream_t st) {
   kw_query<8, 3><<<query_grid(c, n, 8), 256, 8 * W_SLOT_BYTES, st>>>(n, states, actions, nullptr, c->d_cards, c->d_wt);

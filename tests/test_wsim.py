@@ -95,6 +95,10 @@ def test_observation_and_features_vs_reference(wsim):
         assert err == 0 and np.array_equal(obs, z["obs"][i]), i
         f, err = wsim.features(st)
         assert err == 0 and np.array_equal(f, z["feat"][i]), i
+        obs, err = wsim.observe_packed(st)  # the streaming forms (no unpack) behind sb_observe / sb_features
+        assert err == 0 and np.array_equal(obs, z["obs"][i]), i
+        f, err = wsim.features_packed(st)
+        assert err == 0 and np.array_equal(f, z["feat"][i]), i
 
 
 def test_decisions_and_heuristic_games(oracle, wsim):

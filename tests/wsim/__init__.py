@@ -72,9 +72,19 @@ def features(st):
     return f, lib().wsim_features(_p(st), _p(f))
 
 
+def features_packed(st):
+    f = np.zeros(10, dtype=np.float64)
+    return f, lib().wsim_features_packed(_p(st), _p(f))
+
+
 def observe(st):
     obs = np.zeros((27, 5, 4), dtype=np.int32)
     return obs, lib().wsim_observe(_p(st), _p(obs))
+
+
+def observe_packed(st):
+    obs = np.zeros((27, 5, 4), dtype=np.int32)
+    return obs, lib().wsim_observe_packed(_p(st), _p(obs))
 
 
 def expert_action(st):

@@ -68,11 +68,19 @@ int wsim_features(const uint8_t* state, double* f) {
   w_scan_badobs(&wg);
   return w_features(&wg, f);
 }
+int wsim_features_packed(const uint8_t* state, double* f) {  // the streaming form: no unpack
+  init_once();
+  return w_features_packed((const SbState*)state, g_cards, f);
+}
 int wsim_observe(const uint8_t* state, int32_t* obs) {
   init_once();
   WG wg; wg_init(&wg);
   w_unpack(&wg, (const SbState*)state);
   return w_observe(&wg, obs);
+}
+int wsim_observe_packed(const uint8_t* state, int32_t* obs) {  // the streaming form: no unpack
+  init_once();
+  return w_observe_packed((const SbState*)state, g_cards, obs);
 }
 int wsim_expert_action(uint8_t* state) {
   init_once();

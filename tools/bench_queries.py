@@ -23,8 +23,9 @@ for n in (4096, 65536, 1048576):
         name = "thread" if engine_id == 0 else "warp  "
         rows = [("legal_mask", lambda: eng.legal_mask(st), 512 + 20), ("features", lambda: eng.features(st), 512 + 80),
                 ("expert_action", lambda: eng.expert_action(st.clone()), 512 + 4)]
+        rows += [("observe", lambda: eng.observe(st), 512 + 2160)]
         if n <= 65536:
-            rows += [("observe", lambda: eng.observe(st), 512 + 2160), ("select_action", lambda: eng.select_action(st, w), 512 + 81)]
+            rows += [("select_action", lambda: eng.select_action(st, w), 512 + 81)]
         for what, f, bytes_per in rows:
             ms = timed(f)
             print("%s %-14s n=%8d  %8.3f ms  %8.1f M games/s  %7.1f GB/s" % (name, what, n, ms, n / ms / 1e3, bytes_per * n / ms / 1e6), flush=True)
