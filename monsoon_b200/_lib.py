@@ -8,7 +8,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libsb_b200.so")
+SO_PATH = os.environ.get("SB_LIB") or os.path.join(HERE, "libsb_b200.so")  # SB_LIB: development builds (tools/build_variant.sh)
 
 _vp = ctypes.c_void_p
 _int = ctypes.c_int
