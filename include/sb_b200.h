@@ -133,6 +133,24 @@ int sb_rollout_heuristic(SbHandle *h, int n, uint8_t *states_d, const double *w_
 int sb_accumulate_fitness(SbHandle *h, int n, const int8_t *result_d, const int32_t *idx_first_d, int32_t *counts_d,
                           void *stream);
 
+/* The evaluation schedule on the device (evo/fitness.py:52-59 pairings, :100-121 games per pairing): game index
+ * game_lo + t -> idx_first_d[t], idx_second_d[t] (rows of the weight table) and seeds_d[t] for t < n.  A pairing plays
+ * games_per_pair consecutive games.  mode 0 = the reference's round robin: ordered pairs (i, j), i < n_ind, j < n_total,
+ * j != i (rows n_ind.. are the hall of fame); mode 1 = every individual as FIRST against each of the n_total - n_ind fixed
+ * opponents; mode 2 = (i, i), for a SECOND seat played by expert_action.  seeds are the partition-invariant hash of
+ * (base_seed, generation, i, j, replicate) (the reference seeds every game from OS entropy). */
+int sb_eval_schedule(SbHandle *h, int mode, int n_ind, int n_total, int games_per_pair, uint64_t base_seed, uint32_t generation,
+                     int64_t game_lo, int n, int32_t *idx_first_d, int32_t *idx_second_d, uint64_t *seeds_d, void *stream);
+
+/* FitnessEvaluator.evaluate_population (evo/fitness.py:32-121) for the games [game_lo, game_hi) of a schedule (a rank's shard),
+ * entirely on the device: sb_eval_schedule -> sb_reset (decks_d u8[2,n_deck] shared by all games, factions_d u8[2]) ->
+ * sb_rollout_heuristic over weights_d f64[n_total,10] -> sb_accumulate_fitness into counts_d i32[n_ind,3] (+=) and
+ * sb_count_aborted into aborted_d i32[2] (+=, nullable), chunk_games at a time (<= 0: 262,144) in a workspace owned by the
+ * handle.  Asynchronous on `stream`; nothing is copied to the host. */
+int sb_eval_population(SbHandle *h, int mode, int n_ind, int n_total, int games_per_pair, uint64_t base_seed, uint32_t generation,
+                       int64_t game_lo, int64_t game_hi, const double *weights_d, const uint8_t *decks_d, int n_deck,
+                       const uint8_t *factions_d, int max_steps, int chunk_games, int32_t *counts_d, int32_t *aborted_d, void *stream);
+
 /* Games a rollout aborted (result -2), split by cause: out_d i32[2] += {games stopped by an exception the reference raises
  * too (state.err 1..4; evo/fitness.py:208-210 scores them as a draw as well), games stopped by a limit of this engine
  * (state.err 5..7: SB_ERR_UNSUPPORTED / OVERFLOW / DEPTH -- the reference would have kept playing)}.  The evaluator

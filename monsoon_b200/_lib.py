@@ -43,6 +43,9 @@ SIGNATURES = {
     "sb_rollout_heuristic": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "sb_accumulate_fitness": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
     "sb_count_aborted": (_int, [_vp, _int, _vp, _vp, _vp, _vp]),
+    "sb_eval_schedule": (_int, [_vp, _int, _int, _int, _int, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int64, _int, _vp, _vp, _vp, _vp]),
+    "sb_eval_population": (_int, [_vp, _int, _int, _int, _int, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int64, ctypes.c_int64, _vp, _vp, _int, _vp,
+                                  _int, _int, _vp, _vp, _vp]),
     "sb_step_host": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_rollout_random_host": (_int, [_vp, _int, _vp, _vp, _int, _vp, _int, _vp, _vp, _vp]),
 }

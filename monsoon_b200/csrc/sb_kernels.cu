@@ -609,6 +609,33 @@ __global__ void k_count_aborted(int n, const u8* states, const i8* result, int* 
   atomicAdd(&out[code >= SB_ERR_UNSUPPORTED ? 1 : 0], 1);
 }
 
+// The evaluation schedule on the device (evo/fitness.py:52-59,100-121): game index -> (FIRST individual, SECOND individual,
+// seed).  A pairing plays games_per_pair consecutive games; pairings are enumerated
+//   mode 0  round robin: (i, j) for i < n_ind, j < n_total, j != i, row-major (everyone against everyone and the hall of fame)
+//   mode 1  versus: (i, n_ind + b) for i < n_ind, b < n_total - n_ind (every individual against fixed opponents)
+//   mode 2  solo: (i, i) (the SECOND seat is the scripted opponent)
+// seed = the partition-invariant hash of (base seed, generation, i, j, replicate) that evo.game_seed computes on the host.
+__global__ void k_eval_schedule(int mode, int n_ind, int n_total, int gpp, unsigned long long base_seed, unsigned int generation,
+                                long long g_lo, int n, int* idx_first, int* idx_second, unsigned long long* seeds) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const long long gi = g_lo + t;
+  const long long p = gi / gpp;
+  const unsigned long long k = (unsigned long long)(gi % gpp);
+  long long i, j;
+  if (mode == 0) { const long long per = n_total - 1; i = p / per; const long long r = p % per; j = r < i ? r : r + 1; }
+  else if (mode == 1) { const long long per = n_total - n_ind; i = p / per; j = n_ind + p % per; }
+  else { i = p; j = p; }
+  const unsigned long long M = 0x7FFFFFFFFFFFFFFFull;
+  unsigned long long x = (base_seed * 0x9E3779B97F4A7C15ull + (unsigned long long)generation * 0xBF58476D1CE4E5B9ull +
+                          (unsigned long long)i * 0x94D049BB133111EBull + (unsigned long long)j * 0xD6E8FEB86659FD93ull + k) & M;
+  x ^= x >> 31;
+  x = (x * 0x2545F4914F6CDD1Dull) & M;
+  idx_first[t] = (int)i;
+  idx_second[t] = (int)j;
+  seeds[t] = x;
+}
+
 // ================================================================ host side / C ABI
 #include "sb_card_table_host.h"
 
@@ -621,6 +648,7 @@ struct SbHandle {
   char err[256];
   // staging for the *_host entry points
   u8* d_stage; size_t stage_bytes;
+  u8* d_eval; size_t eval_bytes;  // workspace of sb_eval_population (states, schedule, results of one chunk)
   cudaStream_t stream;
   int gpw;  // games per warp for the thread-per-game shape (0 = choose by batch size)
   int turn_sync;   // 1: turn-synchronous warp schedule in the rollout kernel
@@ -830,6 +858,7 @@ int sb_destroy(SbHandle* h) {
   if (h->d_pool_n) cudaFree(h->d_pool_n);
   if (h->d_arch) cudaFree(h->d_arch);
   if (h->d_stage) cudaFree(h->d_stage);
+  if (h->d_eval) cudaFree(h->d_eval);
   if (h->stream) cudaStreamDestroy(h->stream);
   free(h);
   return 0;
@@ -1063,6 +1092,60 @@ int sb_count_aborted(SbHandle* h, int n, const uint8_t* states_d, const int8_t* 
   return 0;
 }
 
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int sb_eval_schedule(SbHandle* h, int mode, int n_ind, int n_total, int games_per_pair, uint64_t base_seed, uint32_t generation,
+                     int64_t game_lo, int n, int32_t* idx_first_d, int32_t* idx_second_d, uint64_t* seeds_d, void* stream) {
+  DEV_GUARD(h);
+  if (n <= 0) return 0;
+  if (mode < 0 || mode > 2 || n_ind <= 0 || games_per_pair <= 0 || n_total < n_ind || (mode == 0 && n_total < 2) || (mode == 1 && n_total == n_ind)) {
+    snprintf(h->err, sizeof(h->err), "sb_eval_schedule: bad schedule (mode %d, %d individuals, %d rows, %d games per pairing)", mode, n_ind,
+             n_total, games_per_pair);
+    return 1;
+  }
+  k_eval_schedule<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(mode, n_ind, n_total, games_per_pair, (unsigned long long)base_seed, generation,
+                                                                    (long long)game_lo, n, idx_first_d, idx_second_d, (unsigned long long*)seeds_d);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+// One evaluation = schedule -> new games -> whole heuristic games -> counts, chunk by chunk on `stream`, nothing on the host in
+// between (no synchronisation: the caller reads counts_d when it needs them).
+int sb_eval_population(SbHandle* h, int mode, int n_ind, int n_total, int games_per_pair, uint64_t base_seed, uint32_t generation,
+                       int64_t game_lo, int64_t game_hi, const double* weights_d, const uint8_t* decks_d, int n_deck, const uint8_t* factions_d,
+                       int max_steps, int chunk_games, int32_t* counts_d, int32_t* aborted_d, void* stream) {
+  DEV_GUARD(h);
+  if (game_hi <= game_lo) return 0;
+  if (chunk_games <= 0) chunk_games = 262144;
+  const int64_t total = game_hi - game_lo;
+  const int cap = (int)(total < chunk_games ? total : chunk_games);
+  const size_t o_states = 0, o_seed = al256((size_t)cap * SB_STATE_BYTES), o_i1 = o_seed + al256((size_t)cap * 8), o_i2 = o_i1 + al256((size_t)cap * 4),
+               o_res = o_i2 + al256((size_t)cap * 4), bytes = o_res + al256((size_t)cap);
+  if (h->eval_bytes < bytes) {
+    if (h->d_eval) cudaFree(h->d_eval);
+    h->d_eval = nullptr; h->eval_bytes = 0;
+    CK(cudaMalloc(&h->d_eval, bytes));
+    h->eval_bytes = bytes;
+  }
+  u8* d = h->d_eval;
+  for (int64_t c0 = game_lo; c0 < game_hi; c0 += cap) {
+    const int n = (int)(game_hi - c0 < cap ? game_hi - c0 : cap);
+    int32_t* i1 = (int32_t*)(d + o_i1);
+    int32_t* i2 = (int32_t*)(d + o_i2);
+    int rc = sb_eval_schedule(h, mode, n_ind, n_total, games_per_pair, base_seed, generation, c0, n, i1, i2, (uint64_t*)(d + o_seed), stream);
+    if (rc) return rc;
+    rc = sb_reset(h, n, (const uint64_t*)(d + o_seed), decks_d, n_deck, 1, factions_d, d + o_states, stream);
+    if (rc) return rc;
+    rc = sb_rollout_heuristic(h, n, d + o_states, weights_d, mode == 2 ? nullptr : weights_d, i1, mode == 2 ? nullptr : i2, max_steps,
+                              (int8_t*)(d + o_res), nullptr, stream);
+    if (rc) return rc;
+    rc = sb_accumulate_fitness(h, n, (const int8_t*)(d + o_res), i1, counts_d, stream);
+    if (rc) return rc;
+    if (aborted_d) { rc = sb_count_aborted(h, n, d + o_states, (const int8_t*)(d + o_res), aborted_d, stream); if (rc) return rc; }
+  }
+  return 0;
+}
+
 // ---------------------------------------------------------------- host-buffer (e2e) variants
 static int ensure_stage(SbHandle* h, size_t bytes) {
   if (h->stage_bytes >= bytes) return 0;
@@ -1072,8 +1155,6 @@ static int ensure_stage(SbHandle* h, size_t bytes) {
   h->stage_bytes = bytes;
   return 0;
 }
-static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
-
 int sb_step_host(SbHandle* h, int n, uint8_t* states, const uint8_t* actions, int8_t* reward, uint8_t* done, uint8_t* err,
                  uint32_t* next_masks) {
   DEV_GUARD(h);

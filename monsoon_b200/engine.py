@@ -241,6 +241,37 @@ class Engine:
                     "sb_count_aborted")
         return out
 
+    SCHEDULES = {"round_robin": 0, "versus": 1, "solo": 2}
+
+    def eval_schedule(self, mode, n_ind, n_total, games_per_pair, base_seed, generation, game_lo, n):
+        """sb_eval_schedule: (idx_first i32[n], idx_second i32[n], seeds i64[n]) of the games game_lo .. game_lo + n - 1"""
+        i1 = torch.empty(n, dtype=torch.int32, device=self.device)
+        i2 = torch.empty(n, dtype=torch.int32, device=self.device)
+        seeds = torch.empty(n, dtype=torch.int64, device=self.device)
+        self._check(self.lib.sb_eval_schedule(self.h, self.SCHEDULES[mode], n_ind, n_total, games_per_pair, int(base_seed) & 0xFFFFFFFFFFFFFFFF,
+                                              int(generation), int(game_lo), n, self._p(i1), self._p(i2), self._p(seeds), self._stream()),
+                    "sb_eval_schedule")
+        return i1, i2, seeds
+
+    def eval_population(self, mode, n_ind, weights, games_per_pair, base_seed, generation, game_lo, game_hi, max_steps=400,
+                        counts=None, aborted=None, chunk_games=0):
+        """sb_eval_population over the default decks: counts i32[n_ind,3] += {wins, draws, losses}, aborted i32[2] += ...; asynchronous."""
+        weights = self._dev(weights, torch.float64)
+        assert weights.dim() == 2 and weights.shape[1] == 10 and weights.shape[0] >= n_ind, "weight tables are f64[P, 10] (SB_N_FEATURES)"
+        if self._default_decks is None:
+            self._default_decks = (torch.tensor([deck_indices(d) for d in DEFAULT_DECKS], dtype=torch.uint8, device=self.device),
+                                   torch.tensor(DEFAULT_FACTIONS, dtype=torch.uint8, device=self.device))
+        decks, factions = self._default_decks
+        counts = counts if counts is not None else torch.zeros((n_ind, 3), dtype=torch.int32, device=self.device)
+        aborted = aborted if aborted is not None else torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._dev(counts, torch.int32)
+        assert counts.numel() >= 3 * n_ind
+        self._check(self.lib.sb_eval_population(self.h, self.SCHEDULES[mode], n_ind, weights.shape[0], games_per_pair,
+                                                int(base_seed) & 0xFFFFFFFFFFFFFFFF, int(generation), int(game_lo), int(game_hi), self._p(weights),
+                                                self._p(decks), decks.shape[-1], self._p(factions), max_steps, int(chunk_games), self._p(counts),
+                                                self._p(aborted), self._stream()), "sb_eval_population")
+        return counts, aborted
+
     # ------------------------------------------------------------------ host-buffer (e2e) entry points
     def step_host(self, states_np, actions_np, want_masks=True):
         """numpy in, numpy out; H2D + kernel + D2H inside the call (sb_step_host)."""

@@ -313,25 +313,28 @@ class FitnessEvaluator:
 
     def evaluate_population(self, population, generation=0):
         n = len(population)
-        all_opponents = list(population)
-        if self.use_hall_of_fame and len(self.hall_of_fame) > 0:
-            all_opponents.extend(self.hall_of_fame)
+        hof = list(self.hall_of_fame) if self.use_hall_of_fame else []
+        if torch.is_tensor(population):  # resident rows (training.Population.w): the table never visits the host
+            all_opponents = torch.cat([population, self._weight_table(hof, population.device)]) if hof else population
+        else:
+            all_opponents = list(population) + hof
         n_total = len(all_opponents)
         g = int(self.config.games_per_pairing)
-        pairs = self.pairings(n, n_total)
+        pairs = self.pairings(n, n_total) if (self.reference_faithful or n_total < 2) else None
+        n_pairs = n * (n_total - 1)
         start = time.time()
-        if self.reference_faithful or not pairs:
+        if self.reference_faithful or not n_pairs:
             # evo/fitness.py:193,217: the loop never runs and `False == 0` credits the row player (Q15)
             counts = np.zeros((n, 3), dtype=np.int64)
-            for i, _j in pairs:
+            for i, _j in pairs or []:
                 counts[i, 0] += g
         else:
-            counts = self._play(population, all_opponents, pairs, g, generation)
+            counts = self._play(population, all_opponents, None, g, generation, schedule="round_robin")
         self.last_counts = counts
         scores = counts[:, 0] * 1.0 + counts[:, 1] * 0.5
         per_individual = (n_total - 1) * g  # evo/fitness.py:112 (Q20 normalisation kept)
         fitness = [float(s) / per_individual if per_individual else 0.0 for s in scores]
-        self.total_games += len(pairs) * g
+        self.total_games += n_pairs * g
         self.total_time += time.time() - start
         self._update_hall_of_fame(population, fitness)
         return fitness
@@ -342,11 +345,14 @@ class FitnessEvaluator:
         returns (wins + 0.5 draws) / games per individual."""
         n = len(population)
         g = int(games_per_opponent or self.config.games_per_pairing)
-        pairs = [(i, n + b) for i in range(n) for b in range(len(opponents))]
         start = time.time()
-        counts = self._play(population, list(population) + list(opponents), pairs, g, generation)
+        if torch.is_tensor(population):  # resident weight tables (training.Population.w): no host detour
+            table = torch.cat([population, self._weight_table(opponents, population.device)])
+        else:
+            table = list(population) + list(opponents)
+        counts = self._play(population, table, None, g, generation, schedule="versus")
         self.last_counts = counts
-        self.total_games += len(pairs) * g
+        self.total_games += n * len(opponents) * g
         self.total_time += time.time() - start
         per = len(opponents) * g
         return [float(c[0] + 0.5 * c[1]) / per for c in counts]
@@ -357,50 +363,72 @@ class FitnessEvaluator:
         n = len(population)
         g = int(games or self.config.games_per_pairing)
         start = time.time()
-        counts = self._play(population, list(population), [(i, i) for i in range(n)], g, generation, expert_second=True)
+        counts = self._play(population, population if torch.is_tensor(population) else list(population), None, g, generation, expert_second=True,
+                            schedule="solo")
         self.last_counts = counts
         self.total_games += n * g
         self.total_time += time.time() - start
         return [float(c[0] + 0.5 * c[1]) / g for c in counts]
 
-    def _play(self, population, all_opponents, pairs, g, generation, expert_second=False):
+    @staticmethod
+    def _weight_table(vectors, dev):
+        """rows of a weight table: a list of WeightVectors, or a resident f64[n, 10] tensor (training.Population.w) used as it is"""
+        if torch.is_tensor(vectors):
+            return vectors.to(device=dev, dtype=torch.float64).contiguous()
+        return torch.as_tensor(np.stack([np.asarray(v.weights, dtype=np.float64) for v in vectors])).to(dev)
+
+    def _play(self, population, all_opponents, pairs, g, generation, expert_second=False, schedule=None):
+        """schedule: "round_robin" / "versus" / "solo" when `pairs` is that standard enumeration -- the device derives pair indices
+        and seeds itself (sb_eval_population) and nothing but the weight table crosses the bus; None: `pairs` as given."""
         import torch.distributed as dist
         eng = self._engine()
         dev = eng.device
         dist_on = dist.is_available() and dist.is_initialized()
         rank, world = (dist.get_rank(), dist.get_world_size()) if dist_on else (0, 1)
-        w = torch.as_tensor(np.stack([np.asarray(v.weights, dtype=np.float64) for v in all_opponents])).to(dev)
+        w = self._weight_table(all_opponents, dev)
         if dist_on:
             dist.broadcast(w, src=0)  # population weights from rank 0
-        n_games = len(pairs) * g
+        n_ind = len(population)
+        n_pairs = len(pairs) if pairs is not None else {"round_robin": n_ind * (w.shape[0] - 1), "versus": n_ind * (w.shape[0] - n_ind),
+                                                       "solo": n_ind}[schedule]
+        n_games = n_pairs * g
         lo, hi = self.shard(n_games, rank, world)
-        pair_arr = np.asarray(pairs, dtype=np.int64)
         base_seed = int(getattr(self.config, "seed", 0) or 0)
         max_steps = int(self.config.max_turns)
-        counts = torch.zeros((len(population), 3), dtype=torch.int32, device=dev)
+        counts = torch.zeros((n_ind, 3), dtype=torch.int32, device=dev)
         aborted = torch.zeros(2, dtype=torch.int32, device=dev)
-        for c0 in range(lo, hi, self.chunk_games):
-            c1 = min(hi, c0 + self.chunk_games)
-            gi = np.arange(c0, c1, dtype=np.int64)
-            pi, k = gi // g, gi % g
-            i_idx, j_idx = pair_arr[pi, 0], pair_arr[pi, 1]
-            seeds = game_seed_array(base_seed, generation, i_idx, j_idx, k)
-            idx_first = torch.as_tensor(i_idx.astype(np.int32)).to(dev)
-            idx_second = torch.as_tensor(j_idx.astype(np.int32)).to(dev)
-            seeds_d = torch.as_tensor(seeds).to(dev)
-            if self.deck_config is not None:  # evo/fitness.py:136-141: generation-aware decks, drawn per game
-                decks, factions = self.deck_config.generate_batch(eng, seeds_d, generation)
-                states = eng.reset(seeds_d, decks, factions)
-            else:
-                states = eng.reset(seeds_d)
-            result, _steps = eng.rollout_heuristic(states, w, None if expert_second else w, idx_first, None if expert_second else idx_second,
-                                                   max_steps=max_steps)
-            eng.accumulate_fitness(result, idx_first, counts)
-            eng.count_aborted(states, result, aborted)
+        if schedule is not None and self.deck_config is None:
+            eng.eval_population(schedule, n_ind, w, g, base_seed, generation, lo, hi, max_steps=max_steps, counts=counts, aborted=aborted,
+                                chunk_games=self.chunk_games)
+        else:
+            pair_arr = np.asarray(pairs, dtype=np.int64) if pairs is not None else None
+            for c0 in range(lo, hi, self.chunk_games):
+                c1 = min(hi, c0 + self.chunk_games)
+                if schedule is not None:
+                    idx_first, idx_second, seeds_d = eng.eval_schedule(schedule, n_ind, w.shape[0], g, base_seed, generation, c0, c1 - c0)
+                else:
+                    gi = np.arange(c0, c1, dtype=np.int64)
+                    pi, k = gi // g, gi % g
+                    i_idx, j_idx = pair_arr[pi, 0], pair_arr[pi, 1]
+                    seeds = game_seed_array(base_seed, generation, i_idx, j_idx, k)
+                    idx_first = torch.as_tensor(i_idx.astype(np.int32)).to(dev)
+                    idx_second = torch.as_tensor(j_idx.astype(np.int32)).to(dev)
+                    seeds_d = torch.as_tensor(seeds).to(dev)
+                if self.deck_config is not None:  # evo/fitness.py:136-141: generation-aware decks, drawn per game
+                    decks, factions = self.deck_config.generate_batch(eng, seeds_d, generation)
+                    states = eng.reset(seeds_d, decks, factions)
+                else:
+                    states = eng.reset(seeds_d)
+                result, _steps = eng.rollout_heuristic(states, w, None if expert_second else w, idx_first, None if expert_second else idx_second,
+                                                       max_steps=max_steps)
+                eng.accumulate_fitness(result, idx_first, counts)
+                eng.count_aborted(states, result, aborted)
         if dist_on:
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM)  # integer counts: order-independent, bit-exact
-            dist.all_reduce(aborted, op=dist.ReduceOp.SUM)
-        ab = aborted.cpu().numpy()
+            both = torch.cat([counts.view(-1), aborted])  # one collective: integer counts are order-independent, bit-exact
+            dist.all_reduce(both, op=dist.ReduceOp.SUM)
+            counts, aborted = both[:-2].view(n_ind, 3), both[-2:]
+        host = torch.cat([counts.view(-1), aborted]).cpu().numpy()  # the one device-to-host read of an evaluation
+        ab = host[-2:]
         self.last_aborted = (int(ab[0]), int(ab[1]))
         self.total_aborted[0] += int(ab[0])
         self.total_aborted[1] += int(ab[1])
@@ -408,7 +436,7 @@ class FitnessEvaluator:
             import warnings
             warnings.warn("%d of %d games stopped at a capacity limit of the engine (SB_ERR_UNSUPPORTED/OVERFLOW/DEPTH) and were "
                           "scored as draws" % (int(ab[1]), n_games))
-        return counts.cpu().numpy().astype(np.int64)
+        return host[:-2].reshape(n_ind, 3).astype(np.int64)
 
     def get_stats(self):
         return {"total_games": self.total_games, "total_time": self.total_time,
@@ -427,7 +455,16 @@ class FitnessEvaluator:
 
     def _update_hall_of_fame(self, population, fitness):  # evo/fitness.py:247-259
         pairs = sorted(zip(fitness, range(len(population))), key=lambda x: x[0], reverse=True)
-        self.hall_of_fame = [population[i].copy() for _f, i in pairs[:self.hall_of_fame_size]]
+        top = [i for _f, i in pairs[:self.hall_of_fame_size]]
+        if torch.is_tensor(population):  # resident rows: only the winners come to the host (sigmas are not part of an opponent)
+            rows = population[torch.as_tensor(top, device=population.device)].cpu().numpy() if top else []
+            self.hall_of_fame = []
+            for r in rows:
+                v = WeightVector.__new__(WeightVector)
+                v.weights, v.sigmas, v.size = r.copy(), np.zeros_like(r), len(r)
+                self.hall_of_fame.append(v)
+        else:
+            self.hall_of_fame = [population[i].copy() for i in top]
 
 
 def play_game(adapter, agent1, agent2, max_turns=400):

@@ -249,10 +249,11 @@ class Population:
     def _seed(self):
         return int(self.config.seed or 0)
 
-    def generate_offspring(self):
+    def generate_offspring(self, materialize=True):
+        """materialize=False: the offspring stay rows mu.. of the resident tables (the generation loop uses them there)"""
         c = self.config
         self.eng.es_offspring(self._seed(), self.generation, c.mu, c.lambda_, c.tau, c.tau_prime, c.min_sigma, self.w, self.s)
-        return self._vectors(self.w[c.mu:].cpu().numpy(), self.s[c.mu:].cpu().numpy())
+        return self._vectors(self.w[c.mu:].cpu().numpy(), self.s[c.mu:].cpu().numpy()) if materialize else None
 
     def select_from_combined(self, all_individuals, fitness_scores):
         """Top-mu of parents + offspring, then the two repair steps of evo/population.py:128-170.  `all_individuals`
@@ -363,9 +364,11 @@ class EvolutionEngine:
         """One pass of the loop body of evo/evolution.py:77-110; returns the generation wall time."""
         t0 = time.time()
         pop = self.population
-        everyone = pop.get_parents()
+        # parents (+ offspring) as rows of the resident weight table: weights never leave the device inside the loop
+        everyone = pop.w[:self.config.mu]
         if pop.generation > 0:
-            everyone = everyone + pop.generate_offspring()
+            pop.generate_offspring(materialize=False)
+            everyone = pop.w[:self.config.mu + self.config.lambda_]
         fitness = self._evaluate(everyone, pop.generation)
         if pop.generation == 0:
             pop.fitness_scores = fitness

@@ -227,3 +227,32 @@ def test_evolutionary_stormbound(engine):
     g.reset()
     assert g.get_phase_info()["phase"] == "Explore" and len(g.player1_deck) == 12
     assert isinstance(g.expert_agent(), int) and g.action_to_string(155) == "Pass the turn"
+
+
+@pytest.mark.gpu
+def test_device_schedule_matches_host_pairings(engine):
+    """sb_eval_schedule == the reference-shaped pairing lists (evo/fitness.py:52-59) + the scalar seed hash, for every mode and any shard"""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_host_logic import OracleEngine
+    for mode, n_ind, n_total, g in (("round_robin", 5, 5, 3), ("round_robin", 4, 9, 2), ("round_robin", 1, 3, 4), ("versus", 6, 8, 3), ("solo", 7, 7, 5)):
+        n_pairs = {"round_robin": n_ind * (n_total - 1), "versus": n_ind * (n_total - n_ind), "solo": n_ind}[mode]
+        for lo, n in ((0, n_pairs * g), (3, n_pairs * g - 4)):
+            i1, i2, seeds = engine.eval_schedule(mode, n_ind, n_total, g, 123456789, 7, lo, n)
+            w1, w2, ws = OracleEngine.host_schedule(mode, n_ind, n_total, g, 123456789, 7, lo, n)
+            assert np.array_equal(i1.cpu().numpy(), w1) and np.array_equal(i2.cpu().numpy(), w2) and np.array_equal(seeds.cpu().numpy(), ws), (mode, lo)
+
+
+@pytest.mark.gpu
+def test_eval_population_entry_matches_stepwise_calls(engine):
+    """sb_eval_population (one call, chunked, device-side schedule) == schedule + reset + rollout + accumulate issued one by one"""
+    rs = np.random.RandomState(11)
+    w = torch.from_numpy(rs.uniform(0, 1, (7, 10))).to(engine.device)
+    for mode, n_ind in (("round_robin", 7), ("versus", 5), ("solo", 7)):
+        n_games = {"round_robin": 7 * 6, "versus": 5 * 2, "solo": 7}[mode] * 3
+        counts, aborted = engine.eval_population(mode, n_ind, w, 3, 99, 2, 1, n_games - 2, chunk_games=16)
+        i1, i2, seeds = engine.eval_schedule(mode, n_ind, 7, 3, 99, 2, 1, n_games - 3)
+        st = engine.reset(seeds)
+        res, _ = engine.rollout_heuristic(st, w, None if mode == "solo" else w, i1, None if mode == "solo" else i2)
+        want = engine.accumulate_fitness(res, i1, torch.zeros((n_ind, 3), dtype=torch.int32, device=engine.device))
+        assert torch.equal(counts, want) and int(counts.sum()) == n_games - 3

@@ -104,6 +104,29 @@ class OracleEngine:
                 out[1 if st[18] >= 5 else 0] += 1
         return out
 
+    @staticmethod
+    def host_schedule(mode, n_ind, n_total, g, base_seed, generation, lo, n):
+        """what sb_eval_schedule computes, from the reference-shaped pairing LISTS and the scalar seed hash"""
+        from monsoon_b200.evo import FitnessEvaluator, game_seed
+        pairs = {"round_robin": FitnessEvaluator.pairings(n_ind, n_total), "versus": [(i, n_ind + b) for i in range(n_ind) for b in range(n_total - n_ind)],
+                 "solo": [(i, i) for i in range(n_ind)]}[mode]
+        rows = [(pairs[gi // g][0], pairs[gi // g][1], game_seed(base_seed, generation, pairs[gi // g][0], pairs[gi // g][1], gi % g)) for gi in range(lo, lo + n)]
+        return (np.array([r[0] for r in rows], dtype=np.int32), np.array([r[1] for r in rows], dtype=np.int32), np.array([r[2] for r in rows], dtype=np.int64))
+
+    def eval_schedule(self, mode, n_ind, n_total, g, base_seed, generation, lo, n):
+        import torch
+        return tuple(torch.from_numpy(a) for a in self.host_schedule(mode, n_ind, n_total, g, base_seed, generation, lo, n))
+
+    def eval_population(self, mode, n_ind, weights, g, base_seed, generation, lo, hi, max_steps=400, counts=None, aborted=None, chunk_games=0):
+        chunk = chunk_games or 262144
+        for c0 in range(lo, hi, chunk):
+            i1, i2, seeds = self.eval_schedule(mode, n_ind, weights.shape[0], g, base_seed, generation, c0, min(hi, c0 + chunk) - c0)
+            states = self.reset(seeds)
+            res, _ = self.rollout_heuristic(states, weights, weights, i1, i2, max_steps)
+            self.accumulate_fitness(res, i1, counts)
+            self.count_aborted(states, res, aborted)
+        return counts, aborted
+
 
 def _deck_schedule():
     from monsoon_b200.evo import DeckEvolutionConfig

@@ -21,8 +21,10 @@ def run(name, P, opponents, gpo):
     pop = [vec(w) for w in np.random.RandomState(42).uniform(0, 1, (P, 10))]
     opp = [vec(w) for w in np.random.RandomState(7).uniform(0, 1, (opponents, 10))]
     ev = FitnessEvaluator(Cfg(), device=lr)
+    if os.environ.get("EVO_RESIDENT", "1") == "1":  # the weight table of training.Population: resident f64[P, 10]
+        pop = torch.from_numpy(np.stack([v.weights for v in pop])).to(torch.device("cuda", lr))
     out = []
-    for gen in range(3):
+    for gen in range(4):
         torch.cuda.synchronize()
         if world > 1: dist.barrier()
         t0 = time.perf_counter()
