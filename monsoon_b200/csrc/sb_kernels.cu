@@ -591,6 +591,258 @@ __global__ void __launch_bounds__(WPC * 32, BSYNC ? 1 : (HEUR_MIN_CTAS * 4) / WP
   }
 }
 
+// ---------------------------------------------------------------- heuristic rollout, K games per warp
+// The kernel above gives a whole warp to one game: a decision offers 18.6 candidates on average (oracle statistics over
+// default-deck games: median 16, 20 % of the decisions forced), so 40 % of the lanes have nothing to fork, every lane still
+// copies the base and recomputes the legal mask and the base features, and 2,048 resident threads per SM at 32 registers
+// spill into the same local memory the forks live in.  Here a warp owns K games.  Lane q < K is the OWNER of slot q: it
+// loads / retires the game, computes its legal mask and base features once (shared memory), and applies the chosen action.
+// The candidates of all K games are numbered consecutively and dealt to the 32 lanes round by round, so the lanes are
+// busy whatever the games' candidate counts are; the arg-max is a segmented warp reduction (first maximum = lowest action
+// id, like np.argmax).  The winner is re-applied to the base by the owner lane (one extra step per decision instead of
+// keeping 32 forks alive).  A quarter of the threads for the same number of games in flight: 3-4x the registers per
+// thread and a quarter of the call frames.  Same results as k_rollout_heuristic, game for game.
+struct __align__(8) PSlot { double w[2][SB_N_FEATURES]; double fc[SB_N_FEATURES]; u32 mask[SB_MASK_WORDS]; int cerr, seat, fc_valid, n_legal; };  // n_legal >= 0: mask is this decision's legal set
+// The base state of a slot between decisions, in shared memory: what copy_g moves, stored WITHOUT the unused pool slots (a
+// base has at most 20 entities: end_of_step compacts beyond that, unpack creates at most that): 1.2 KB instead of the 1.9 KB of
+// a whole G, so that twice the warps fit an SM.  The block [board .. trig) keeps G's layout: `view()` reads its scalars in place.
+#define IMG_BLOCK ((int)(offsetof(G, trig) - offsetof(G, board)))
+struct __align__(8) Img {
+  unsigned char block[IMG_BLOCK];
+  Ent e[SB_N_TILES];
+  Mem mem[NMEM];
+  SBD_FI const G& view() const { return *reinterpret_cast<const G*>(block - offsetof(G, board)); }  // fields of [board .. trig) only
+};
+#define PACK_BYTES(K) ((int)((K) * (sizeof(Img) + sizeof(PSlot))))
+SBD_NI void img_store(Img& dst, const G& src) {  // src.n_ent <= 20 (after end_of_step / unpack)
+  typedef unsigned long long u64;
+  static_assert(IMG_BLOCK % 8 == 0 && offsetof(Img, e) % 8 == 0 && offsetof(Img, mem) % 8 == 0, "Img layout");
+  const u64* s8 = reinterpret_cast<const u64*>(&src);
+  u64* blk = reinterpret_cast<u64*>(dst.block) - offsetof(G, board) / 8;  // blk[i] is word i of a G
+  const int p0 = (int)(offsetof(G, pl) / 8), pw = (int)(sizeof(Ply) / 8), dk = (int)(offsetof(Ply, deck) / 8);
+  const int e0 = p0 + dk + src.pl[0].n_deck, e1 = p0 + pw + dk + src.pl[1].n_deck;
+#pragma unroll 4
+  for (int i = (int)(offsetof(G, board) / 8); i < e0; i++) blk[i] = s8[i];
+#pragma unroll 4
+  for (int i = p0 + pw; i < e1; i++) blk[i] = s8[i];
+#pragma unroll
+  for (int i = p0 + 2 * pw; i < (int)(offsetof(G, trig) / 8); i++) blk[i] = s8[i];
+  u64* d8 = reinterpret_cast<u64*>(dst.e);
+  const int ne = (src.n_ent < SB_N_TILES ? src.n_ent : SB_N_TILES) * (int)(sizeof(Ent) / 8);
+#pragma unroll 4
+  for (int i = 0; i < ne; i++) d8[i] = s8[i];
+  u64* m8 = reinterpret_cast<u64*>(dst.mem);
+  const int m0 = (int)(offsetof(G, mem) / 8), nm = src.n_mem * (int)(sizeof(Mem) / 8);
+#pragma unroll 1
+  for (int i = 0; i < nm; i++) m8[i] = s8[m0 + i];
+}
+SBD_NI void img_load(G& dst, const Img& src) {
+  typedef unsigned long long u64;
+  u64* d8 = reinterpret_cast<u64*>(&dst);
+  const G& v = src.view();
+  const u64* blk = reinterpret_cast<const u64*>(src.block) - offsetof(G, board) / 8;
+  const int p0 = (int)(offsetof(G, pl) / 8), pw = (int)(sizeof(Ply) / 8), dk = (int)(offsetof(Ply, deck) / 8);
+  const int e0 = p0 + dk + v.pl[0].n_deck, e1 = p0 + pw + dk + v.pl[1].n_deck;
+#pragma unroll 4
+  for (int i = (int)(offsetof(G, board) / 8); i < e0; i++) d8[i] = blk[i];
+#pragma unroll 4
+  for (int i = p0 + pw; i < e1; i++) d8[i] = blk[i];
+#pragma unroll
+  for (int i = p0 + 2 * pw; i < (int)(offsetof(G, trig) / 8); i++) d8[i] = blk[i];
+  const u64* s8 = reinterpret_cast<const u64*>(src.e);
+  const int ne = v.n_ent * (int)(sizeof(Ent) / 8);
+#pragma unroll 4
+  for (int i = 0; i < ne; i++) d8[i] = s8[i];
+  const u64* m8 = reinterpret_cast<const u64*>(src.mem);
+  const int m0 = (int)(offsetof(G, mem) / 8), nm = v.n_mem * (int)(sizeof(Mem) / 8);
+#pragma unroll 1
+  for (int i = 0; i < nm; i++) d8[m0 + i] = m8[i];
+}
+SBD_FI void img_commit(Img& b, G& g) { end_of_step(g); img_store(b, g); }  // same lazy compaction / overflow rules as the random rollout
+SBD_FI int nth_action(const u32* m, int k) {
+#pragma unroll 1
+  for (int wd = 0; wd < SB_MASK_WORDS; wd++) {
+    const int c = __popc(m[wd]);
+    if (k < c) { u32 v = m[wd]; for (int q = 0; q < k; q++) v &= v - 1; return wd * 32 + __ffs(v) - 1; }
+    k -= c;
+  }
+  return SB_ACTION_PASS;
+}
+template <int K, int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB) k_rollout_heuristic_packed(int n, u8* states, const double* w_first, const double* w_second,
+                                                                             const int* idx_first, const int* idx_second, int max_steps, i8* result,
+                                                                             int* steps_out, const DCard* cards, const double* wt, int* queue) {
+  __shared__ DCard s_cards[SBC_COUNT];
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  stage_cards(s_cards, cards);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Img* base = reinterpret_cast<Img*>(s_dyn + (size_t)warp * PACK_BYTES(K));
+  PSlot* ps = reinterpret_cast<PSlot*>(base + K);
+  G g;
+  init_g(g, s_cards, wt);
+  const bool owner = lane < K;
+  Img& b = base[owner ? lane : 0];
+  const G& bv = b.view();
+  PSlot& me = ps[owner ? lane : 0];
+  int gi = -1, steps = 0;
+  bool alive = false, aborted = false, exhausted = false;
+#pragma unroll 1
+  for (;;) {
+    // ---- owner lanes: retire a finished game, take the next one from the queue
+    if (owner) {
+#pragma unroll 1
+      for (;;) {
+        if (alive) {
+          const bool l0 = bv.pl[0].base < 0, l1 = bv.pl[1].base < 0;
+          if (!(aborted || steps >= max_steps || l0 || l1)) break;
+          __align__(16) SbState s;
+          img_load(g, b);
+          pack(g, s);
+          store_state(states + (size_t)gi * SB_STATE_BYTES, s);
+          if (result) result[gi] = (i8)(aborted ? -2 : (l1 && !l0) ? 0 : (l0 && !l1) ? 1 : -1);
+          if (steps_out) steps_out[gi] = steps;
+          alive = false;
+        }
+        if (exhausted) break;
+        gi = atomicAdd(queue, 1);
+        if (gi >= n) { exhausted = true; break; }
+        __align__(16) SbState s;
+        load_state(s, states + (size_t)gi * SB_STATE_BYTES);
+        unpack(g, s);
+        scan_badobs(g);
+        img_store(b, g);
+        if (w_first) {
+          const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
+          for (int k = 0; k < SB_N_FEATURES; k++) me.w[0][k] = pf[k];
+        }
+        if (w_second) {
+          const double* pw = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
+          for (int k = 0; k < SB_N_FEATURES; k++) me.w[1][k] = pw[k];
+        }
+        me.fc_valid = 0; me.n_legal = -1;
+        steps = 0; aborted = false; alive = true;
+      }
+    }
+    if (!__ballot_sync(0xFFFFFFFFu, owner && alive)) break;
+    // ---- phase 1, owner lanes: legal set and base features of the slot's decision
+    int n_cand = 0, forced = -1;
+    bool expert = false;
+    if (owner && alive) {
+      const bool first = bv.player_sign == 1;
+      expert = first ? (w_first == nullptr) : (w_second == nullptr);
+      if (!expert) {
+        int n_legal = me.n_legal;  // >= 0: left, with the mask, by the lane that committed the last action
+        const bool need_fc = !me.fc_valid;
+        if (n_legal < 0 || need_fc) img_load(g, b);
+        if (n_legal < 0) {
+          u32 m[SB_MASK_WORDS];
+          legal_mask(g, m);
+          n_legal = 0;
+#pragma unroll
+          for (int i = 0; i < SB_MASK_WORDS; i++) { n_legal += __popc(m[i]); me.mask[i] = m[i]; }
+        }
+        me.seat = first ? 0 : 1;
+        if (n_legal > 1) {
+          if (need_fc) {  // else: the committed fork's features (same mover, same perspective)
+            double fc[SB_N_FEATURES];
+            me.cerr = features(g, fc);
+#pragma unroll
+            for (int i = 0; i < SB_N_FEATURES; i++) me.fc[i] = fc[i];
+          }
+          n_cand = n_legal;
+        } else forced = n_legal == 1 ? nth_action(me.mask, 0) : SB_ACTION_PASS;  // forced move: argmax of one (none: PASS)
+      }
+    }
+    __syncwarp();
+    // ---- phase 2: the candidates of all slots, numbered consecutively, 32 per round
+    int incl = n_cand;
+#pragma unroll
+    for (int off = 1; off < K; off <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off); if (lane >= off) incl += t; }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, K - 1);
+    const int excl = incl - n_cand;
+    Best mine; mine.score = 0.0; mine.action = -1;
+    int held_k = -1, held_a = -1, held_err = 1;  // the fork this lane still holds after the rounds (its last candidate)
+    double fn[SB_N_FEATURES];
+#pragma unroll 1
+    for (int r0 = 0; r0 < total; r0 += 32) {
+      const int c = r0 + lane;
+      int k = -1, j = 0;
+#pragma unroll
+      for (int q = 0; q < K; q++) {
+        const int e = __shfl_sync(0xFFFFFFFFu, excl, q), nc = __shfl_sync(0xFFFFFFFFu, n_cand, q);
+        if (c >= e && c < e + nc) { k = q; j = c - e; }
+      }
+      double sc = 0.0;
+      int a = -1;
+      if (k >= 0) {
+        const PSlot& p = ps[k];
+        a = nth_action(p.mask, j);
+        img_load(g, base[k]);
+        game_step(g, a);
+        int nerr = g.err;
+        if (!nerr) nerr = features(g, fn);
+        if (!nerr && !p.cerr) sc = score_delta(p.w[p.seat], p.fc, fn);
+        held_k = k; held_a = a; held_err = nerr;
+      }
+      // segmented arg-max: one warp reduction per slot present in this round; the owner keeps the first maximum
+#pragma unroll
+      for (int q = 0; q < K; q++) {
+        const int e = __shfl_sync(0xFFFFFFFFu, excl, q), nc = __shfl_sync(0xFFFFFFFFu, n_cand, q);
+        if (nc == 0 || e + nc <= r0 || e >= r0 + 32) continue;  // uniform
+        Best t;
+        t.score = k == q ? sc : 0.0;
+        t.action = k == q ? a : -1;
+        t = warp_argmax(t);
+        if (lane == q && t.action >= 0 && (mine.action < 0 || t.score > mine.score)) mine = t;
+      }
+    }
+    // ---- phase 3: the lane that still holds the winner's fork makes it the game (and leaves its features as the next
+    // decision's base features when the same seat moves again); the owner lane applies forced and expert moves and the
+    // winners nobody holds any more (decisions of more than one round)
+    int chosen = -1;
+    if (owner && alive && !expert) chosen = forced >= 0 ? forced : (mine.action < 0 ? SB_ACTION_PASS : mine.action);
+    const int want = __shfl_sync(0xFFFFFFFFu, chosen, held_k < 0 ? 0 : held_k);  // the action slot held_k plays
+    const bool scored = __shfl_sync(0xFFFFFFFFu, (int)(n_cand > 0), held_k < 0 ? 0 : held_k) != 0;
+    bool holder = held_k >= 0 && scored && held_a == want;
+    // (a candidate appears once per decision, so at most one lane holds a slot's winner)
+    u32 done_slots = 0;
+#pragma unroll
+    for (int q = 0; q < K; q++) if (__ballot_sync(0xFFFFFFFFu, holder && held_k == q)) done_slots |= 1u << q;
+    if (holder) {
+      PSlot& p = ps[held_k];
+      const bool same_seat = held_a != SB_ACTION_PASS && !held_err && !g.err;
+      img_commit(base[held_k], g);
+      {  // the committed state is in this lane's hands: leave the next decision's legal set with it
+        u32 m[SB_MASK_WORDS];
+        legal_mask(g, m);
+        int nl = 0;
+#pragma unroll
+        for (int i = 0; i < SB_MASK_WORDS; i++) { nl += __popc(m[i]); p.mask[i] = m[i]; }
+        p.n_legal = nl;
+      }
+      p.fc_valid = same_seat ? 1 : 0;
+      if (same_seat) {
+#pragma unroll
+        for (int i = 0; i < SB_N_FEATURES; i++) p.fc[i] = fn[i];
+        p.cerr = 0;
+      }
+    }
+    __syncwarp();
+    if (owner && alive) {
+      if (!((done_slots >> lane) & 1u)) {
+        img_load(g, b);
+        const int action = expert ? expert_action(g) : chosen;
+        game_step(g, action);
+        img_commit(b, g);
+        me.fc_valid = 0; me.n_legal = -1;
+      }
+      steps++;
+      if (bv.err) aborted = true;
+    }
+    __syncwarp();
+  }
+}
+
 __global__ void k_accumulate_fitness(int n, const i8* result, const int* idx_first, int* counts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -662,6 +914,7 @@ struct SbHandle {
   int heur_iw;     // heuristic rollout, independent warps: warps per CTA (4, 8, 16; -1 = auto)
   int heur_grid;   // persistent CTAs in refill mode (tests: a grid much smaller than the batch); 0 = one wave
   int heur_refill; // -1 auto, 0 off, 1 on: a warp whose game ended takes the next game from a counter
+  int heur_pack;   // heuristic rollout with K games per warp (k_rollout_heuristic_packed): 0 off, 2 / 4 / 8; -1 auto
   int* d_queue;
   int engine;      // -1 auto, 0 thread-per-game kernels (sb_engine.cuh), 1 warp-per-game kernels (sbw_*.cuh)
   int w_shape;     // warp engine, random rollout: -1 auto, 0/1/2 = CTA shapes of sbw_rollout_random
@@ -818,6 +1071,14 @@ int sb_create(int device, SbHandle** out) {
   CK(cudaFuncSetAttribute(k_rollout_heuristic<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(32 * sizeof(G))));
   CK(cudaFuncSetAttribute(k_rollout_heuristic<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * sizeof(G))));
   CK(cudaFuncSetAttribute(k_rollout_heuristic<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(G))));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic_packed<8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PACK_BYTES(8)));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic_packed<4, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PACK_BYTES(4)));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic_packed<2, 8, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * PACK_BYTES(2)));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic_packed<2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * PACK_BYTES(2)));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic_packed<1, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * PACK_BYTES(1)));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic_packed<1, 8, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * PACK_BYTES(1)));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic_packed<1, 8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * PACK_BYTES(1)));
+  CK(cudaFuncSetAttribute(k_rollout_heuristic_packed<1, 4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * PACK_BYTES(1)));
   CK(cudaFuncSetAttribute(k_rollout_heuristic<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * sizeof(G))));
   CK(cudaFuncSetAttribute(k_rollout_heuristic<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * sizeof(G))));
   CK(cudaFuncSetAttribute(k_rollout_heuristic<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * sizeof(G))));
@@ -841,7 +1102,7 @@ int sb_create(int device, SbHandle** out) {
   }
   h->refill = -1;
   h->dense = -1;
-  h->heur_iw = -1;
+  h->heur_iw = -1; h->heur_pack = -1;
   h->heur_refill = -1;
   CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   const char* env = getenv("SB_GPW");
@@ -1030,6 +1291,7 @@ int sb_set_option(SbHandle* h, const char* key, int value) {
   if (!strcmp(key, "refill_ctas")) { h->refill_ctas = value; return 0; }
   if (!strcmp(key, "refill_grid")) { h->refill_grid = value; return 0; }
   if (!strcmp(key, "heur_iw")) { h->heur_iw = value; return 0; }
+  if (!strcmp(key, "heur_pack")) { h->heur_pack = value; return 0; }
   if (!strcmp(key, "heur_grid")) { h->heur_grid = value; return 0; }
   if (!strcmp(key, "heur_refill")) { h->heur_refill = value; return 0; }
   if (!strcmp(key, "engine")) { h->engine = value; return 0; }
@@ -1047,6 +1309,29 @@ int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_
   if (use_warp_engine(h, WK_ROLLOUT_HEUR, n)) {
     sbw_rollout_heuristic(&h->wctx, n, states_d, w_first_d, w_second_d, idx_first_d, idx_second_d, max_steps, result_d, steps_d,
                           h->w_hshape < 0 ? 0 : h->w_hshape, h->w_grid, st);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  const int pack = h->heur_pack < 0 ? 0 : h->heur_pack;
+  if (pack >= 1) {  // K games per warp, persistent grid
+    int* q = h->d_queue + 1;
+    cudaMemsetAsync(q, 0, sizeof(int), st);
+#define HPACK(K, W, B) do { const int full = grid_for(n, (K) * (W)), resident = h->sm_count * (B); \
+    const int grid = h->heur_grid > 0 ? h->heur_grid : (full < resident ? full : resident); \
+    k_rollout_heuristic_packed<K, W, B><<<grid, (W) * 32, (W) * PACK_BYTES(K), st>>>(n, states_d, w_first_d, w_second_d, idx_first_d, idx_second_d, \
+                                                                               max_steps, (i8*)result_d, steps_d, h->d_cards, h->d_wt, q); } while (0)
+    // measured shapes (tools/sweep_heur_pack.py): K games per warp x warps per CTA x CTAs per SM
+    switch (pack) {
+      case 8: HPACK(8, 4, 4); break;   // 16 warps
+      case 4: HPACK(4, 4, 8); break;   // 32 warps, 64 registers
+      case 3: HPACK(2, 8, 6); break;   // 48 warps, 40 registers
+      case 1: HPACK(1, 8, 8); break;   // 64 warps, 32 registers
+      case 5: HPACK(1, 8, 6); break;   // 48 warps, 40 registers
+      case 6: HPACK(1, 8, 4); break;   // 32 warps, 64 registers
+      case 7: HPACK(1, 4, 16); break;  // 64 warps in 4-warp CTAs
+      default: HPACK(2, 8, 8); break;  // 64 warps, 32 registers
+    }
+#undef HPACK
     LAUNCH_CHECK();
     return 0;
   }

@@ -274,3 +274,48 @@ def test_heuristic_vs_expert_with_warp_refill(engine):
             engine.set_option("heur_grid", 0)
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("pack,grid", [(1, 0), (2, 0), (3, 0), (4, 0), (8, 0), (4, 3), (8, 5), (1, 7)])
+def test_heuristic_games_packed_warps(engine, pack, grid):
+    """K games per warp (k_rollout_heuristic_packed: candidates of K games dealt to the 32 lanes, segmented arg-max, the owner
+    lane re-applies the winner): the 1,024 whole reference HeuristicAgent games again, also from a grid far smaller than the batch."""
+    z = load("heuristic_games.npz")
+    dev = engine.device
+    try:
+        engine.set_option("heur_pack", pack)
+        engine.set_option("heur_grid", grid)
+        st = engine.reset(torch.from_numpy(z["seeds"].astype(np.int64)).to(dev))
+        res, steps = engine.rollout_heuristic(st, torch.from_numpy(z["w_first"]).to(dev), torch.from_numpy(z["w_second"]).to(dev), max_steps=400)
+        res, steps, host = res.cpu().numpy(), steps.cpu().numpy(), st.cpu().numpy()
+    finally:
+        for k, v in (("heur_pack", -1), ("heur_grid", 0)):
+            engine.set_option(k, v)
+    assert np.array_equal(res, z["result"])
+    ok = z["result"] != -2
+    assert np.array_equal(steps[ok], z["lengths"][ok])
+    host[:, 19] = 0
+    assert np.array_equal(fnv1a64_rows(host[ok]), z["final"][ok])
+
+
+def test_heuristic_vs_expert_packed_warps(engine):
+    """Packed shape with one seat handed to the scripted opponent, and random decks (all cards): identical to the one-game-per-warp kernel."""
+    dev = engine.device
+    seeds = torch.arange(3000, dtype=torch.int64, device=dev) + 777
+    w = torch.from_numpy(np.random.RandomState(5).uniform(0, 1, (3000, 10))).to(dev)
+    fac = torch.from_numpy(np.random.RandomState(9).randint(1, 5, (3000, 2)).astype(np.uint8)).to(dev)
+    decks, factions = engine.generate_decks(seeds, 0, 3, factions=fac)
+    out = []
+    for pack in (0, 1, 2, 4, 8):
+        try:
+            engine.set_option("heur_pack", pack)
+            st = engine.reset(seeds)
+            res, steps = engine.rollout_heuristic(st, w, None, max_steps=400)
+            st2 = engine.reset(seeds, decks, factions)
+            res2, steps2 = engine.rollout_heuristic(st2, w, w, max_steps=150)
+            out.append(tuple(x.cpu().numpy() for x in (res, steps, st, res2, steps2, st2)))
+        finally:
+            engine.set_option("heur_pack", -1)
+    for other in out[1:]:
+        for a, b in zip(out[0], other):
+            assert np.array_equal(a, b)
