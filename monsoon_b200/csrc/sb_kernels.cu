@@ -668,6 +668,22 @@ SBD_FI int nth_action(const u32* m, int k) {
   }
   return SB_ACTION_PASS;
 }
+// once per game, out of line: keeps the decision loop's instruction lines dense
+SBD_NI void slot_retire(G& g, const Img& b, u8* record) {
+  __align__(16) SbState s;
+  img_load(g, b);
+  pack(g, s);
+  store_state(record, s);
+}
+SBD_NI void slot_load(G& g, Img& b, PSlot& me, const u8* record, const double* pf, const double* pw) {
+  __align__(16) SbState s;
+  load_state(s, record);
+  unpack(g, s);
+  scan_badobs(g);
+  img_store(b, g);
+  if (pf) for (int k = 0; k < SB_N_FEATURES; k++) me.w[0][k] = pf[k];
+  if (pw) for (int k = 0; k < SB_N_FEATURES; k++) me.w[1][k] = pw[k];
+}
 template <int K, int WPC, int MINB>
 __global__ void __launch_bounds__(WPC * 32, MINB) k_rollout_heuristic_packed(int n, u8* states, const double* w_first, const double* w_second,
                                                                              const int* idx_first, const int* idx_second, int max_steps, i8* result,
@@ -695,10 +711,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_rollout_heuristic_packed(int
         if (alive) {
           const bool l0 = bv.pl[0].base < 0, l1 = bv.pl[1].base < 0;
           if (!(aborted || steps >= max_steps || l0 || l1)) break;
-          __align__(16) SbState s;
-          img_load(g, b);
-          pack(g, s);
-          store_state(states + (size_t)gi * SB_STATE_BYTES, s);
+          slot_retire(g, b, states + (size_t)gi * SB_STATE_BYTES);
           if (result) result[gi] = (i8)(aborted ? -2 : (l1 && !l0) ? 0 : (l0 && !l1) ? 1 : -1);
           if (steps_out) steps_out[gi] = steps;
           alive = false;
@@ -706,19 +719,8 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_rollout_heuristic_packed(int
         if (exhausted) break;
         gi = atomicAdd(queue, 1);
         if (gi >= n) { exhausted = true; break; }
-        __align__(16) SbState s;
-        load_state(s, states + (size_t)gi * SB_STATE_BYTES);
-        unpack(g, s);
-        scan_badobs(g);
-        img_store(b, g);
-        if (w_first) {
-          const double* pf = w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES;
-          for (int k = 0; k < SB_N_FEATURES; k++) me.w[0][k] = pf[k];
-        }
-        if (w_second) {
-          const double* pw = w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES;
-          for (int k = 0; k < SB_N_FEATURES; k++) me.w[1][k] = pw[k];
-        }
+        slot_load(g, b, me, states + (size_t)gi * SB_STATE_BYTES, w_first ? w_first + (size_t)(idx_first ? idx_first[gi] : gi) * SB_N_FEATURES : nullptr,
+                  w_second ? w_second + (size_t)(idx_second ? idx_second[gi] : gi) * SB_N_FEATURES : nullptr);
         me.fc_valid = 0; me.n_legal = -1;
         steps = 0; aborted = false; alive = true;
       }
@@ -796,50 +798,52 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_rollout_heuristic_packed(int
         if (lane == q && t.action >= 0 && (mine.action < 0 || t.score > mine.score)) mine = t;
       }
     }
-    // ---- phase 3: the lane that still holds the winner's fork makes it the game (and leaves its features as the next
-    // decision's base features when the same seat moves again); the owner lane applies forced and expert moves and the
-    // winners nobody holds any more (decisions of more than one round)
+    // ---- phase 3: ONE lane per slot ends up with the post-action state in its private working set -- the lane that still
+    // holds the winner's fork, else the owner lane (forced and expert moves, winners of an earlier round) after applying the
+    // action to a fresh copy of the base.  That lane commits the state and, while it has it at hand, prepares the slot's next
+    // decision: legal set and base features (the fork's own features when the same seat moves again).
     int chosen = -1;
     if (owner && alive && !expert) chosen = forced >= 0 ? forced : (mine.action < 0 ? SB_ACTION_PASS : mine.action);
     const int want = __shfl_sync(0xFFFFFFFFu, chosen, held_k < 0 ? 0 : held_k);  // the action slot held_k plays
     const bool scored = __shfl_sync(0xFFFFFFFFu, (int)(n_cand > 0), held_k < 0 ? 0 : held_k) != 0;
-    bool holder = held_k >= 0 && scored && held_a == want;
-    // (a candidate appears once per decision, so at most one lane holds a slot's winner)
+    // a candidate appears once per decision: at most one lane per slot.  An owner lane may hold its own slot's winner only: it
+    // may have to apply that slot's action itself below
+    bool holder = held_k >= 0 && scored && held_a == want && (lane >= K || held_k == lane);
     u32 done_slots = 0;
 #pragma unroll
     for (int q = 0; q < K; q++) if (__ballot_sync(0xFFFFFFFFu, holder && held_k == q)) done_slots |= 1u << q;
+    bool have_fn = holder && !held_err;
+    if (owner && alive && !((done_slots >> lane) & 1u)) {
+      img_load(g, b);
+      held_a = expert ? expert_action(g) : chosen;
+      game_step(g, held_a);
+      held_k = lane; holder = true; have_fn = false;
+    }
     if (holder) {
       PSlot& p = ps[held_k];
-      const bool same_seat = held_a != SB_ACTION_PASS && !held_err && !g.err;
       img_commit(base[held_k], g);
-      {  // the committed state is in this lane's hands: leave the next decision's legal set with it
+      p.n_legal = -1; p.fc_valid = 0;
+      const bool next_first = g.player_sign == 1;
+      if (!g.err && (next_first ? w_first != nullptr : w_second != nullptr)) {
         u32 m[SB_MASK_WORDS];
         legal_mask(g, m);
         int nl = 0;
 #pragma unroll
         for (int i = 0; i < SB_MASK_WORDS; i++) { nl += __popc(m[i]); p.mask[i] = m[i]; }
         p.n_legal = nl;
-      }
-      p.fc_valid = same_seat ? 1 : 0;
-      if (same_seat) {
+        if (nl > 1) {
+          if (!(have_fn && held_a != SB_ACTION_PASS)) p.cerr = features(g, fn); else p.cerr = 0;
 #pragma unroll
-        for (int i = 0; i < SB_N_FEATURES; i++) p.fc[i] = fn[i];
-        p.cerr = 0;
+          for (int i = 0; i < SB_N_FEATURES; i++) p.fc[i] = fn[i];
+          p.fc_valid = 1;
+        }
       }
     }
     __syncwarp();
     if (owner && alive) {
-      if (!((done_slots >> lane) & 1u)) {
-        img_load(g, b);
-        const int action = expert ? expert_action(g) : chosen;
-        game_step(g, action);
-        img_commit(b, g);
-        me.fc_valid = 0; me.n_legal = -1;
-      }
       steps++;
       if (bv.err) aborted = true;
     }
-    __syncwarp();
   }
 }
 
@@ -1312,7 +1316,7 @@ int sb_rollout_heuristic(SbHandle* h, int n, uint8_t* states_d, const double* w_
     LAUNCH_CHECK();
     return 0;
   }
-  const int pack = h->heur_pack < 0 ? 0 : h->heur_pack;
+  const int pack = h->heur_pack < 0 ? 1 : h->heur_pack;  // auto: one game per warp in the owner / holder structure (faster at every batch size, tools/sweep_heur_pack.py)
   if (pack >= 1) {  // K games per warp, persistent grid
     int* q = h->d_queue + 1;
     cudaMemsetAsync(q, 0, sizeof(int), st);
