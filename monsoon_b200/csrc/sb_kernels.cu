@@ -462,6 +462,7 @@ SBD_NI int decide(G& g, Base* base, const double* w, double* scores_out, bool co
     if (n_legal == 1 && !scores_out) { best.score = 0.0; best.action = a; break; }  // forced move: argmax of one
     if (dirty) base_load(g, *base);
     game_step(g, a);
+    end_of_step(g);  // a candidate that leaves more than the packed layout holds is an engine status, like for the state that gets committed
     dirty = true; last = a;
     double sc = 0.0;
     int nerr = g.err;
@@ -781,6 +782,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) k_rollout_heuristic_packed(int
         a = nth_action(p.mask, j);
         img_load(g, base[k]);
         game_step(g, a);
+        end_of_step(g);  // a candidate that leaves more than the packed layout holds is an engine status, like for the state that gets committed
         int nerr = g.err;
         if (!nerr) nerr = features(g, fn);
         if (!nerr && !p.cerr) sc = score_delta(p.w[p.seat], p.fc, fn);

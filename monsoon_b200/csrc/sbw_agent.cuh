@@ -40,6 +40,7 @@ SBW_NI int w_decide(WG* base, WG* work, const double* w, double* scores_out, boo
         bits &= bits - 1;
         w_copy_game(work, base);
         w_game_step(work, a);
+        w_end_of_step(work);  // a candidate that leaves more than the packed layout holds is an engine status, like for the committed state
         double sc = 0.0;
         int nerr = work->err;
         if (!nerr) nerr = w_features(work, work->feat);

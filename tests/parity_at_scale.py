@@ -81,3 +81,31 @@ for i in range(NH):
             print("MISMATCH heuristic seed", int(seeds[i]), r, int(g_res[i]), len(acts), int(g_steps[i]))
 print("heuristic agents: %d games, %d env steps, %d mismatches (oracle %.0f s)" % (NH, tot, bad, time.time() - t0), flush=True)
 
+
+# heuristic agents with RANDOM decks (all cards of the pool above): the forks of the evaluation kernel reach every card effect
+# every second game holds UA20 (its copies grow hands and decks beyond the packed layout: the capacity status must come up at the
+# same step in both engines, also when it is a CANDIDATE that overflows)
+NR = max(NH // 2, 100)
+seeds = np.arange(NR, dtype=np.int64) + 1300000
+dd = [rdecks(int(s)) for s in seeds]
+UA20 = [i for i, c in enumerate(CARDS) if c["name"] == "UA20"][0]
+for i in range(1, NR, 2):
+    if UA20 not in dd[i][0][1] and CARDS[UA20]["faction"] in (0, dd[i][1][1]):
+        dd[i][0][1][0] = UA20
+decks = torch.tensor([d for d, _f in dd], dtype=torch.uint8, device=dev); fac = torch.tensor([f for _d, f in dd], dtype=torch.uint8, device=dev)
+st = eng.reset(torch.from_numpy(seeds).to(dev), decks, fac)
+res, steps = eng.rollout_heuristic(st, torch.from_numpy(w1[:NR]).to(dev), torch.from_numpy(w2[:NR]).to(dev), max_steps=400)
+g_res, g_steps, g_host = res.cpu().numpy(), steps.cpu().numpy(), st.cpu().numpy()
+bad = tot = flagged = 0
+t0 = time.time()
+for i in range(NR):
+    d, f = dd[i]
+    s = oracle.new_game(int(seeds[i]), d[0], d[1], f[0], f[1])
+    r, acts = oracle.play_heuristic(s, w1[i], w2[i], 400)
+    tot += len(acts)
+    flagged += r == -2
+    if r != int(g_res[i]) or len(acts) != int(g_steps[i]) or s.tobytes() != g_host[i].tobytes():
+        bad += 1
+        if bad < 5:
+            print("MISMATCH heuristic random decks seed", int(seeds[i]), r, int(g_res[i]), len(acts), int(g_steps[i]))
+print("heuristic agents, random decks: %d games, %d env steps, %d stopped by an engine status in both, %d mismatches (oracle %.0f s)" % (NR, tot, flagged, bad, time.time() - t0), flush=True)

@@ -14,4 +14,4 @@ def test_rollouts_match_oracle_on_fresh_games():
     out = subprocess.run([sys.executable, tool, n], capture_output=True, text=True, timeout=1500)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if "mismatches" in l]
-    assert len(lines) == 3 and all(" 0 mismatches" in l for l in lines), out.stdout[-2000:]
+    assert len(lines) == 4 and all(" 0 mismatches" in l for l in lines), out.stdout[-2000:]
