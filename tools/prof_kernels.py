@@ -2,8 +2,9 @@
 whole-game rollouts (which have their own captures).  Every API is called once untimed first (warm-up, outside the profiled
 range), then once between cudaProfilerStart / Stop.
   thread-per-game: k_reset, k_generate_decks, k_legal_mask, k_observe, k_features, k_expert_action, k_step (1 M games),
-                   k_select_action, k_accumulate_fitness, k_count_aborted, k_es_offspring / select / reset_sigmas / inject_diversity
-  warp-per-game:   kw_query<legal mask / observation / features / expert action>, kw_step, kw_select_action"""
+                   k_select_action, k_accumulate_fitness, k_count_aborted, k_eval_schedule, k_es_offspring / select / reset_sigmas / inject_diversity
+  warp-per-game:   kw_stream<legal mask / observation / features> (streaming, straight from the packed record), kw_query<expert action>,
+                   kw_step, kw_select_action"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT]
@@ -44,6 +45,7 @@ def thread_calls():
     eng.select_action(st_mid[:16384], w_mid)
     eng.accumulate_fitness(res, idx, counts)
     eng.count_aborted(st_mid, res)
+    eng.eval_schedule("round_robin", 256, 261, 4, 1, 0, 0, N_MID)
     eng.es_offspring(1, 1, mu, mu, 0.1, 0.01, 1e-5, esw, ess)
     eng.es_select(mu, fit, esw, ess)
     eng.es_reset_sigmas(1, 1, 0.1, ess[:mu].contiguous())
