@@ -43,7 +43,11 @@ int sb_sm_count(SbHandle *h);
  * "heur_wpc" = -1 / 4: independent warps (default), 8 / 16 / 32: warps per CTA deciding in step; "heur_refill" = -1 auto
  * (batches beyond one wave of resident warps), 0/1: a warp of the heuristic rollout whose game ended takes the next game
  * from a counter; "heur_iw" = -1 auto, 4 / 8 / 16 independent warps per CTA; "heur_grid" = persistent CTAs of that shape
- * (0 = one wave; tests use tiny grids); "lanes_per_game" is accepted and ignored (retired shape). */
+ * (0 = one wave; tests use tiny grids); "lanes_per_game" is accepted and ignored (retired shape).
+ * Round 2: "engine" = -1 auto (measured per-kernel policy), 0 thread-per-game kernels, 1 warp-per-game kernels; "w_shape" /
+ * "w_hshape" / "w_grid" = CTA shape and persistent grid of the warp-per-game rollouts (-1 / 0 = auto); "heur_pack" = -1 auto
+ * (= 1), 0 the round-1 heuristic rollout, 1 one game per warp in the owner / holder structure, 2 / 3 / 4 / 8 several games per
+ * warp (candidates of K games dealt to the 32 lanes), 5 / 6 / 7 other CTA shapes of K = 1.  Every setting gives identical results. */
 int sb_set_option(SbHandle *h, const char *key, int value);
 /* kernels launched through this handle so far (bench.py's gpu_launches) */
 uint64_t sb_launch_count(SbHandle *h);
