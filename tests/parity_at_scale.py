@@ -13,6 +13,8 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 # SB_SCALE_ALL_CARDS=1: also the cards the reference cannot observe / orders by hash (UP01-03, S203): engine vs oracle only
 EXCLUDE = () if os.environ.get("SB_SCALE_ALL_CARDS") else ("UP01", "UP02", "UP03", "S203")
 eng = Engine(0); dev = eng.device
+if os.environ.get("SB_ENGINE"):  # force one engine (0 thread-per-game, 1 warp-per-game) instead of the per-kernel policy
+    eng.set_option("engine", int(os.environ["SB_ENGINE"]))
 FNV = 0x100000001B3; M64 = (1 << 64) - 1
 
 
