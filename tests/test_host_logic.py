@@ -312,3 +312,25 @@ def test_evolutionary_stormbound_mirror_surface():
     have = {n for n in vars(Mirror) if not n.startswith("_") and callable(getattr(Mirror, n))}
     assert want <= have, want - have
     assert "env" not in vars(Mirror) and "env" not in Mirror.__init__.__code__.co_names
+
+
+def test_resident_weight_tables_give_the_same_evaluation():
+    """FitnessEvaluator fed the rows of a resident weight table (what training.Population hands it since round 2) == fed the
+    WeightVector list: fitness, counts and hall of fame, for the round robin (with hall-of-fame opponents in the second
+    generation), the versus schedule and the expert-seat schedule."""
+    import torch
+    from monsoon_b200.evo import FitnessEvaluator, WeightVector
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    np.random.seed(5)
+    pop = [WeightVector(10) for _ in range(3)]
+    table = torch.from_numpy(np.stack([v.weights for v in pop]))
+    a = FitnessEvaluator(Cfg(), engine=OracleEngine(), chunk_games=4)
+    b = FitnessEvaluator(Cfg(), engine=OracleEngine(), chunk_games=1000)
+    for gen in range(2):  # the second generation plays the hall of fame of the first
+        fa, fb = a.evaluate_population(pop, gen), b.evaluate_population(table, gen)
+        assert fa == fb and np.array_equal(a.last_counts, b.last_counts)
+        assert len(a.hall_of_fame) == len(b.hall_of_fame) == 3
+        assert all(np.array_equal(x.weights, y.weights) for x, y in zip(a.hall_of_fame, b.hall_of_fame))
+    opp = [WeightVector(10)]
+    assert a.evaluate_vs(pop, opp, 3, games_per_opponent=2) == b.evaluate_vs(table, opp, 3, games_per_opponent=2)
+    assert np.array_equal(a.last_counts, b.last_counts) and a.last_counts.sum() == 3 * 2
