@@ -150,7 +150,12 @@ def _rank_main(rank, world, port, q):
     fit = ev.evaluate_population(pop, 0)
     ev2 = FitnessEvaluator(Cfg(), deck_config=_deck_schedule(), engine=OracleEngine(), chunk_games=7)  # per-game decks, balance phase
     fit2 = ev2.evaluate_population(pop, 5)
-    q.put((rank, fit, ev.last_counts.tolist(), fit2, ev2.last_counts.tolist()))
+    # the versus schedule over a RESIDENT weight table (device-side schedule, one collective for counts + aborted counters)
+    import torch
+    table = torch.from_numpy(np.stack([v.weights for v in pop]))
+    ev3 = FitnessEvaluator(Cfg(), engine=OracleEngine(), chunk_games=4)
+    fit3 = ev3.evaluate_vs(table, [pop[0]], 2, games_per_opponent=2)
+    q.put((rank, fit, ev.last_counts.tolist(), fit2, ev2.last_counts.tolist(), fit3, ev3.last_counts.tolist()))
     dist.destroy_process_group()
 
 
@@ -165,6 +170,8 @@ def test_two_rank_gloo_matches_single_rank():
     assert single.last_counts.sum() == 3 * 2 * 3
     single2 = FitnessEvaluator(Cfg(), deck_config=_deck_schedule(), engine=OracleEngine(), chunk_games=1000)
     want2 = single2.evaluate_population(pop, 5)
+    single3 = FitnessEvaluator(Cfg(), engine=OracleEngine(), chunk_games=1000)
+    want3 = single3.evaluate_vs(pop, [pop[0]], 2, games_per_opponent=2)
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -177,9 +184,10 @@ def test_two_rank_gloo_matches_single_rank():
     got = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(60)
-    for _rank, fit, counts, fit2, counts2 in got:
+    for _rank, fit, counts, fit2, counts2, fit3, counts3 in got:
         assert fit == want and counts == single.last_counts.tolist()
         assert fit2 == want2 and counts2 == single2.last_counts.tolist()  # decks derive from the game seed: partition-invariant
+        assert fit3 == want3 and counts3 == single3.last_counts.tolist()
 
 
 # ---------------------------------------------------------------- f4: checkpoint / log formats
