@@ -342,3 +342,31 @@ def test_resident_weight_tables_give_the_same_evaluation():
     opp = [WeightVector(10)]
     assert a.evaluate_vs(pop, opp, 3, games_per_opponent=2) == b.evaluate_vs(table, opp, 3, games_per_opponent=2)
     assert np.array_equal(a.last_counts, b.last_counts) and a.last_counts.sum() == 3 * 2
+
+
+def test_state_bridge_round_trip_and_layout(oracle):
+    """monsoon_b200.state (the sb_pack / sb_unpack host bridge of SURVEY 8b): the product's own structured dtype == the oracle-side mirror
+    of include/sb_state.h field by field, unpack -> pack is the identity on records of real games, and the dict says what the record says."""
+    import sb_layout
+    from monsoon_b200 import state as S
+    assert S.STATE_DTYPE.itemsize == 512
+    for name in S.STATE_DTYPE.names:
+        assert S.STATE_DTYPE.fields[name][1] == sb_layout.STATE_DTYPE.fields[name][1], name
+    for name in S.PLAYER_DTYPE.names:
+        assert S.PLAYER_DTYPE.fields[name][1] == sb_layout.PLAYER_DTYPE.fields[name][1], name
+    from test_oracle_golden import default_decks
+    d0, d1 = default_decks()
+    for seed in range(12):
+        st = oracle.new_game(seed, d0, d1, 3, 2)
+        for k in range(60):
+            d = S.unpack_state(st)
+            assert S.pack_state(d).tobytes() == st.tobytes(), (seed, k)
+            r = st.view(sb_layout.STATE_DTYPE)[0]
+            assert d["players"][0]["strength"] == int(r["pl"][0]["base"]) and d["steps"] == k
+            assert sum(e is not None for row in d["board"] for e in row) == int((r["tile"]["card"] != 0).sum())
+            m = oracle.legal_mask(st)
+            legal = [a for a in range(156) if m[a >> 5] >> (a & 31) & 1]
+            oracle.step(st, legal[(seed * 7 + k * 13) % len(legal)])
+            if st[19] & 1 or st[18]:
+                break
+        assert "order 0" in S.render_state(st)
